@@ -1,0 +1,118 @@
+/*
+ * texpresso_b200.h -- C ABI of the B200 (sm_100a) BC1..BC5 encoder / decoder.
+ *
+ * Drop-in boundary for the hot path of jansol/texpresso: the reference has no FFI of its own, its
+ * boundary is the Rust public API in lib/src/lib.rs:38-336.  Every entry point below names the
+ * reference item it replaces; INTEGRATION.md shows the `extern "C"` block a `texpresso-cuda` crate binds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns and pre-sizes every buffer, nothing is retained
+ *     after a call returns (reference: #![no_std] without alloc, lib.rs:25).
+ *   - the reference's only error path is a panic (assert / slice bounds).  Here every function returns
+ *     TXP_OK or a negative TXP_ERR_* code; a binding that wants the reference's contract asserts on != 0.
+ *   - calls are synchronous and thread-safe.  Host-pointer entry points use the calling thread's current
+ *     CUDA device (txp_set_device) and an internal per-device context (streams, pinned staging, device
+ *     scratch).  There is NO CPU fallback: without a usable CUDA device they return TXP_ERR_CUDA.
+ *   - pixel data is RGBA8, row-major, tightly packed (lib.rs:323); blocks are row-major, 8 bytes
+ *     (BC1, BC4) or 16 bytes (BC2, BC3, BC5) each (lib.rs:159-168).
+ */
+#ifndef TEXPRESSO_B200_H
+#define TEXPRESSO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TXP_API __declspec(dllexport)
+#else
+#define TXP_API __attribute__((visibility("default")))
+#endif
+
+/* reference `enum Format`, lib.rs:39-46 (declaration order) */
+enum { TXP_FORMAT_BC1 = 0, TXP_FORMAT_BC2 = 1, TXP_FORMAT_BC3 = 2, TXP_FORMAT_BC4 = 3, TXP_FORMAT_BC5 = 4 };
+
+/* reference `enum Algorithm`, lib.rs:49-59; Default = ClusterFit (lib.rs:61-65) */
+enum { TXP_ALGORITHM_RANGE_FIT = 0, TXP_ALGORITHM_CLUSTER_FIT = 1, TXP_ALGORITHM_ITERATIVE_CLUSTER_FIT = 2 };
+
+enum {
+    TXP_OK = 0,
+    TXP_ERR_FORMAT = -1,           /* format / algorithm value out of range */
+    TXP_ERR_DIMENSIONS = -2,       /* width == 0 (reference: chunks_mut(0) panics) or image too large */
+    TXP_ERR_BUFFER_TOO_SMALL = -3, /* reference: assert!(output.len() >= compressed_size) lib.rs:295, slice panics :138/:324 */
+    TXP_ERR_CUDA = -4,             /* no device / CUDA runtime failure; see txp_last_error() */
+    TXP_ERR_ARGUMENT = -5          /* null pointer, trailing partial block, bad gpu count ... */
+};
+
+/* reference `struct Params`, lib.rs:76-90.  Default (lib.rs:92-100): ClusterFit, PERCEPTUAL, false. */
+typedef struct txp_params {
+    uint32_t algorithm;             /* TXP_ALGORITHM_* */
+    float weights[3];               /* ColourWeights, lib.rs:68; UNIFORM {1,1,1} :71; PERCEPTUAL {0.2126,0.7152,0.0722} :74 */
+    uint32_t weigh_colour_by_alpha; /* bool */
+} txp_params;
+
+/* ---- sizes -------------------------------------------------------------------------------------- */
+TXP_API size_t txp_num_blocks(size_t size);                                   /* num_blocks, lib.rs:103-105 */
+TXP_API size_t txp_block_size(int format);                                    /* Format::block_size, lib.rs:159-168; 0 if bad format */
+TXP_API size_t txp_compressed_size(int format, size_t width, size_t height);  /* Format::compressed_size, lib.rs:175-179 */
+
+/* ---- host-pointer entry points (H2D -> kernels -> D2H inside the call) ----------------------------- */
+
+/* Format::compress, lib.rs:287-335.  Encodes output_len / block_size blocks in block-row-major order;
+ * blocks lying past ceil(height/4) rows are encoded fully masked, as the reference does when `output`
+ * is longer than compressed_size (its loop runs over output.chunks_mut).  rgba_len >= 4*width*height. */
+TXP_API int txp_compress(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height,
+                         const txp_params* params, uint8_t* output, size_t output_len);
+
+/* Format::decompress, lib.rs:124-156.  data_len >= compressed_size, output_len >= 4*width*height. */
+TXP_API int txp_decompress(int format, const uint8_t* data, size_t data_len, size_t width, size_t height,
+                           uint8_t* output, size_t output_len);
+
+/* Format::compress_block_masked, lib.rs:188-234.  mask bit i = pixel i (i = 4*py+px) is valid. */
+TXP_API int txp_compress_block_masked(int format, const uint8_t rgba[64], uint32_t mask,
+                                      const txp_params* params, uint8_t* output, size_t output_len);
+
+/* Format::decompress_block, lib.rs:240-277. */
+TXP_API int txp_decompress_block(int format, const uint8_t* block, size_t block_len, uint8_t output[64]);
+
+/* n independent compress_block_masked / decompress_block calls in one launch
+ * (rgba_blocks: n x 64 bytes, masks: n words, output: n x block_size bytes). */
+TXP_API int txp_compress_blocks(int format, const uint8_t* rgba_blocks, const uint32_t* masks, size_t n,
+                                const txp_params* params, uint8_t* output);
+TXP_API int txp_decompress_blocks(int format, const uint8_t* blocks, size_t n, uint8_t* rgba_blocks);
+
+/* ---- device-pointer entry points (data resident in HBM; asynchronous on `cuda_stream`) ---------------- */
+/* Same semantics as txp_compress / txp_decompress with device pointers on the current device.
+ * cuda_stream is a cudaStream_t (NULL = default stream).  No synchronisation is performed. */
+TXP_API int txp_compress_device(int format, const void* d_rgba, size_t width, size_t height,
+                                const txp_params* params, void* d_output, size_t output_len, void* cuda_stream);
+TXP_API int txp_decompress_device(int format, const void* d_data, size_t width, size_t height,
+                                  void* d_output, size_t output_len, void* cuda_stream);
+
+/* ---- sharding (reference: rayon par_chunks_mut over block rows, lib.rs:300-305 / :128-134) -------------- */
+/* Balanced block-row range [*row_begin, *row_end) of shard `rank` out of `world` for an image of `height`. */
+TXP_API void txp_shard_rows(size_t height, int rank, int world, size_t* row_begin, size_t* row_end);
+
+/* One process, n_gpus devices (0..n_gpus-1): block rows are split with txp_shard_rows, one host worker
+ * per device, each device writes its own slice of `output`.  No collectives. */
+TXP_API int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height,
+                               const txp_params* params, uint8_t* output, size_t output_len, int n_gpus);
+
+/* Batch of independent textures (e.g. mip levels), texture t -> device t % n_gpus. */
+TXP_API int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* widths, const size_t* heights,
+                               size_t n_textures, const txp_params* params, uint8_t* const* outputs, int n_gpus);
+
+/* ---- runtime ------------------------------------------------------------------------------------------ */
+TXP_API int txp_device_count(void);          /* number of CUDA devices, or TXP_ERR_CUDA */
+TXP_API int txp_set_device(int device);      /* cudaSetDevice for the calling thread */
+TXP_API const char* txp_last_error(void);    /* thread-local description of the last failure */
+TXP_API uint64_t txp_kernel_launches(void);  /* kernels launched by this library since load */
+TXP_API const char* txp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXPRESSO_B200_H */

@@ -919,3 +919,14 @@ TXO_API double txo_colour_block_error(int fmt, const uint8_t rgba[64], uint32_t 
     }
     return err;
 }
+
+/* n independent compress_block_masked calls (test convenience; same code path as above) */
+TXO_API void txo_compress_blocks(int fmt, const uint8_t *rgba_blocks, const uint32_t *masks, size_t n, const txo_params *p, uint8_t *out) {
+    size_t bs = block_size(fmt);
+    for (size_t i = 0; i < n; ++i) compress_block_masked(fmt, rgba_blocks + 64 * i, masks[i], p, out + bs * i, NULL);
+}
+
+TXO_API void txo_decompress_blocks(int fmt, const uint8_t *blocks, size_t n, uint8_t *out) {
+    size_t bs = block_size(fmt);
+    for (size_t i = 0; i < n; ++i) decompress_block(fmt, blocks + bs * i, out + 64 * i);
+}

@@ -55,6 +55,10 @@ def lib():
         L.txo_decompress_block.argtypes = [ctypes.c_int, u8p, u8p]
         L.txo_colour_block_error.restype = ctypes.c_double
         L.txo_colour_block_error.argtypes = [ctypes.c_int, u8p, ctypes.c_uint32, ctypes.POINTER(Params), u8p]
+        L.txo_compress_blocks.restype = None
+        L.txo_compress_blocks.argtypes = [ctypes.c_int, u8p, u8p, ctypes.c_size_t, ctypes.POINTER(Params), u8p]
+        L.txo_decompress_blocks.restype = None
+        L.txo_decompress_blocks.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, u8p]
         _lib = L
     return _lib
 
@@ -110,3 +114,22 @@ def colour_block_error(fmt, rgba64, mask, params, block8):
     rgba64 = np.ascontiguousarray(rgba64, dtype=np.uint8).reshape(-1)
     block8 = np.ascontiguousarray(block8, dtype=np.uint8).reshape(-1)
     return lib().txo_colour_block_error(fmt, _ptr(rgba64), mask, ctypes.byref(params), _ptr(block8))
+
+
+def compress_blocks(fmt, rgba_blocks, masks, params=None):
+    rgba_blocks = np.ascontiguousarray(rgba_blocks, dtype=np.uint8).reshape(-1)
+    masks = np.ascontiguousarray(masks, dtype=np.uint32).reshape(-1)
+    n = masks.size
+    assert rgba_blocks.size == 64 * n
+    params = params or make_params()
+    out = np.zeros(n * lib().txo_block_size(fmt), dtype=np.uint8)
+    lib().txo_compress_blocks(fmt, _ptr(rgba_blocks), _ptr(masks), n, ctypes.byref(params), _ptr(out))
+    return out.reshape(n, -1)
+
+
+def decompress_blocks(fmt, blocks):
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1)
+    n = blocks.size // lib().txo_block_size(fmt)
+    out = np.zeros(n * 64, dtype=np.uint8)
+    lib().txo_decompress_blocks(fmt, _ptr(blocks), n, _ptr(out))
+    return out.reshape(n, 16, 4)

@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): bit-exact for RangeFit, SingleColourFit, BC2, the alpha/BC4/BC5 paths and
+all decoders; ClusterFit / IterativeClusterFit >= 99.9 % identical blocks with every differing block no
+worse in the reference's own weighted squared error."""
+import json, pathlib
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+from tests import blockgen
+
+pytestmark = pytest.mark.gpu
+
+KAT = json.loads((pathlib.Path(__file__).parent / "golden" / "kat.json").read_text())
+SETS = sorted(KAT["sets"].items())
+ALGS = [0, 1, 2]
+WEIGHTS = {"uniform": O.UNIFORM, "perceptual": O.PERCEPTUAL, "odd": (0.3, 1.7, 0.05)}
+
+
+@pytest.fixture(scope="module")
+def T():
+    import texpresso_b200 as T
+    assert T.device_count() >= 1
+    return T
+
+
+def _params(T, alg, w, awa=False):
+    return T.Params(T.Algorithm(alg), tuple(w), awa), O.make_params(alg, w, awa)
+
+
+# ---- the reference's own known-answer tests, through the GPU path (lib.rs:363-504) -----------------------
+@pytest.mark.parametrize("alg", ALGS)
+@pytest.mark.parametrize("name,ds", SETS)
+def test_kat_compression(T, name, ds, alg):
+    tp, _ = _params(T, alg, O.UNIFORM)
+    out = T.Format(ds["format"]).compress(np.array(ds["decoded"], np.uint8), 4, 4, tp)
+    assert bytes(out).hex() == bytes(ds["encoded"]).hex()
+
+
+@pytest.mark.parametrize("name,ds", SETS)
+def test_kat_decompression(T, name, ds):
+    out = T.Format(ds["format"]).decompress(np.array(ds["encoded"], np.uint8), 4, 4)
+    assert out.tolist() == ds["decoded"]
+
+
+def test_kat_decode_height_not_multiple_of_4(T):
+    d = KAT["decode_4x6"]
+    out = T.Format(d["format"]).decompress(np.array(d["encoded"], np.uint8), d["width"], d["height"])
+    assert out.reshape(-1, 4).tolist() == [d["pixel"]] * 24
+
+
+# ---- differential layer: stratified blocks through compress_block_masked semantics -----------------------
+def _compare_blocks(T, fmt, blocks, masks, tags, alg, wname, awa):
+    tp, op = _params(T, alg, WEIGHTS[wname], awa)
+    got = T.compress_blocks(fmt, blocks, masks, tp)
+    want = O.compress_blocks(fmt, blocks, masks, op)
+    diff = np.nonzero((got != want).any(axis=1))[0]
+    return got, want, diff, op
+
+
+@pytest.mark.parametrize("awa", [False, True])
+@pytest.mark.parametrize("wname", ["uniform", "perceptual", "odd"])
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_rangefit_blocks_bit_exact(T, fmt, wname, awa):
+    blocks, masks, tags = blockgen.colour_cases()
+    got, want, diff, _ = _compare_blocks(T, fmt, blocks, masks, tags, 0, wname, awa)
+    assert diff.size == 0, [(int(i), tags[i], bytes(got[i]).hex(), bytes(want[i]).hex()) for i in diff[:8]]
+
+
+@pytest.mark.parametrize("awa", [False, True])
+@pytest.mark.parametrize("wname", ["uniform", "perceptual", "odd"])
+@pytest.mark.parametrize("alg", [1, 2])
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_clusterfit_blocks(T, fmt, alg, wname, awa):
+    blocks, masks, tags = blockgen.colour_cases()
+    got, want, diff, op = _compare_blocks(T, fmt, blocks, masks, tags, alg, wname, awa)
+    frac = 1.0 - diff.size / len(blocks)
+    off = 0 if fmt == 0 else 8
+    worse = []
+    for i in diff:
+        # alpha halves must still be bit exact
+        assert bytes(got[i][:off]) == bytes(want[i][:off]), (tags[i], "alpha half differs")
+        eg = O.colour_block_error(fmt, blocks[i], int(masks[i]), op, got[i][off:off + 8])
+        ew = O.colour_block_error(fmt, blocks[i], int(masks[i]), op, want[i][off:off + 8])
+        if eg > ew * (1 + 1e-6) + 1e-12:
+            worse.append((int(i), tags[i], eg, ew, bytes(got[i]).hex(), bytes(want[i]).hex()))
+    assert not worse, worse[:5]
+    assert frac >= 0.999, (frac, [(int(i), tags[i], bytes(got[i]).hex(), bytes(want[i]).hex()) for i in diff[:8]])
+
+
+@pytest.mark.parametrize("fmt", [2, 3, 4])
+def test_alpha_paths_bit_exact(T, fmt):
+    blocks, masks, tags = blockgen.alpha_cases()
+    tp, op = _params(T, 0, O.UNIFORM)
+    got = T.compress_blocks(fmt, blocks, masks, tp)
+    want = O.compress_blocks(fmt, blocks, masks, op)
+    n = 8 if fmt != 4 else 16
+    diff = np.nonzero((got[:, :n] != want[:, :n]).any(axis=1))[0]
+    assert diff.size == 0, [(int(i), tags[i], bytes(got[i]).hex(), bytes(want[i]).hex()) for i in diff[:8]]
+
+
+def test_bc2_alpha_all_values(T):
+    blocks = np.zeros((16, 16, 4), np.uint8)
+    blocks[..., 3] = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    masks = np.full(16, 0xFFFF, np.uint32); masks[5] = 0x0F0F
+    tp, op = _params(T, 0, O.UNIFORM)
+    got = T.compress_blocks(1, blocks, masks, tp)
+    want = O.compress_blocks(1, blocks, masks, op)
+    assert np.array_equal(got, want)
+
+
+def test_single_block_entry_points(T):
+    blocks, masks, tags = blockgen.colour_cases(per_class=2)
+    for i in range(0, len(blocks), 37):
+        for fmt in range(5):
+            tp, op = _params(T, 1, O.PERCEPTUAL)
+            got = T.Format(fmt).compress_block_masked(blocks[i], int(masks[i]), tp)
+            want = O.compress_block_masked(fmt, blocks[i], int(masks[i]), op)
+            assert bytes(got) == bytes(want), (fmt, tags[i])
+            assert np.array_equal(T.Format(fmt).decompress_block(want).reshape(-1), O.decompress_block(fmt, want))
+
+
+# ---- decoders: bit exact on arbitrary (random) blocks -------------------------------------------------------
+@pytest.mark.parametrize("fmt", range(5))
+def test_decode_random_blocks(T, fmt):
+    rng = np.random.default_rng(5 + fmt)
+    bs = 8 if fmt in (0, 3) else 16
+    n = 4096
+    blocks = rng.integers(0, 256, size=(n, bs), dtype=np.uint8)
+    blocks[: n // 4, 0:2] = blocks[: n // 4, 2:4]          # equal endpoints / a0 == a1 cases
+    got = T.decompress_blocks(fmt, blocks)
+    want = O.decompress_blocks(fmt, blocks)
+    assert np.array_equal(got, want)
+
+
+# ---- image layer -----------------------------------------------------------------------------------------------
+SIZES = [(1, 1), (2, 2), (3, 5), (4, 6), (13, 7), (16, 4), (64, 64), (100, 36), (257, 63)]
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("fmt", range(5))
+def test_image_encode_decode(T, fmt, w, h):
+    from texpresso_b200 import synth
+    img = synth.generate("smooth" if (w * h) % 2 else "noise_alpha", w, h, seed=w * 1000 + h)
+    for alg in ((0, 1, 2) if fmt < 3 else (1,)):
+        tp, op = _params(T, alg, O.PERCEPTUAL)
+        got = T.Format(fmt).compress(img, w, h, tp)
+        want = O.compress(fmt, img, w, h, op)
+        assert np.array_equal(got, want), (fmt, alg, w, h)
+    dec = T.Format(fmt).decompress(want, w, h)
+    assert np.array_equal(dec, O.decompress(fmt, want, w, h))
+
+
+@pytest.mark.parametrize("fmt", range(5))
+def test_output_longer_than_needed_encodes_masked_rows(T, fmt):     # SURVEY Q13 (lib.rs:300-334)
+    from texpresso_b200 import synth
+    w, h = 20, 8
+    img = synth.generate("noise_alpha", w, h, seed=3)
+    bs = 8 if fmt in (0, 3) else 16
+    n = T.Format(fmt).compressed_size(w, h) + 2 * 5 * bs + 3 * bs       # two extra rows + a partial row
+    out = np.full(n, 0xEE, np.uint8)
+    tp, op = _params(T, 1, O.PERCEPTUAL)
+    T.Format(fmt).compress(img, w, h, tp, output=out)
+    want = O.compress(fmt, img, w, h, op, out_len=n)
+    assert np.array_equal(out, want)
+
+
+def test_medium_image_all_formats(T):
+    from texpresso_b200 import synth
+    w = h = 256
+    for kind in ("smooth", "noise_alpha", "noise_opaque"):
+        img = synth.generate(kind, w, h, seed=11)
+        for fmt in range(5):
+            for alg in ((0, 1, 2) if fmt < 3 else (1,)):
+                tp, op = _params(T, alg, O.PERCEPTUAL)
+                got = T.Format(fmt).compress(img, w, h, tp)
+                want = O.compress(fmt, img, w, h, op, threads=8)
+                bs = 8 if fmt in (0, 3) else 16
+                nd = int((got.reshape(-1, bs) != want.reshape(-1, bs)).any(axis=1).sum())
+                assert nd == 0, (kind, fmt, alg, nd)
+
+
+# ---- full-size properties (BASELINE.json sizes), oracle only on slices --------------------------------------
+def test_fullsize_8192_bc1_bc3_clusterfit_properties(T):
+    from texpresso_b200 import synth
+    w = h = 8192
+    img = synth.generate("noise_alpha", w, h, seed=3)
+    tp, op = _params(T, 1, O.PERCEPTUAL)
+    for fmt in (0, 2):
+        a = T.Format(fmt).compress(img, w, h, tp)
+        b = T.Format(fmt).compress(img, w, h, tp)
+        assert np.array_equal(a, b), "run-to-run determinism"
+        # block-row shards encode to the same bytes as the whole image (no cross-block state)
+        bs = 8 if fmt == 0 else 16
+        rowbytes = (w // 4) * bs
+        r0, r1 = T.shard_rows(h, 3, 8)
+        part = T.Format(fmt).compress(img[4 * r0:4 * r1], w, 4 * (r1 - r0), tp)
+        assert np.array_equal(part, a[r0 * rowbytes:r1 * rowbytes])
+        # oracle on 8 block rows taken from the middle
+        y0 = 4096
+        want = O.compress(fmt, img[y0:y0 + 32], w, 32, op, threads=8)
+        got = a[(y0 // 4) * rowbytes:(y0 // 4 + 8) * rowbytes]
+        nd = int((got.reshape(-1, bs) != want.reshape(-1, bs)).any(axis=1).sum())
+        assert nd == 0, (fmt, nd)
+        # decoder round trip equals the oracle's decode of the same blocks
+        dec = T.Format(fmt).decompress(a[:rowbytes * 16], w, 64)
+        assert np.array_equal(dec, O.decompress(fmt, a[:rowbytes * 16], w, 64))
+
+
+def test_fullsize_16384_bc4_bc5(T):
+    from texpresso_b200 import synth
+    w = h = 16384
+    img = synth.generate("r_rg", w, h, seed=4)
+    tp, op = _params(T, 1, O.PERCEPTUAL)
+    for fmt in (3, 4):
+        bs = 8 if fmt == 3 else 16
+        a = T.Format(fmt).compress(img, w, h, tp)
+        rowbytes = (w // 4) * bs
+        y0 = 8000
+        want = O.compress(fmt, img[y0:y0 + 64], w, 64, op, threads=8)
+        assert np.array_equal(a[(y0 // 4) * rowbytes:(y0 // 4 + 16) * rowbytes], want)
+        # decode(encode(x)) channel error is bounded by half the largest codebook step (range/5 -> <= 26)
+        dec = T.Format(fmt).decompress(a[:rowbytes * 64], w, 256).reshape(256, w, 4)
+        err = np.abs(dec[..., 0].astype(np.int16) - img[:256, :, 0].astype(np.int16)).max()
+        assert err <= 26
+        del a
+
+
+def test_multi_gpu_matches_single(T):
+    if T.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from texpresso_b200 import synth
+    w, h = 1024, 1000
+    img = synth.generate("smooth", w, h, seed=8)
+    tp, _ = _params(T, 1, O.PERCEPTUAL)
+    for fmt in (0, 2, 4):
+        one = T.Format(fmt).compress(img, w, h, tp)
+        for n in (2, T.device_count()):
+            assert np.array_equal(T.compress_multi(fmt, img, w, h, tp, n_gpus=n), one)

@@ -1,0 +1,200 @@
+"""texpresso_b200 -- B200 (sm_100a) BC1..BC5 encoder/decoder with the library API of jansol/texpresso.
+
+Host-side mirror of the reference's public interface (reference lib/src/lib.rs:38-336), same names and
+argument meaning, over the C ABI in include/texpresso_b200.h:
+
+    Format.Bc1 .. Format.Bc5   .compress / .decompress / .compressed_size / .block_size /
+                               .compress_block_masked / .decompress_block
+    Algorithm.RangeFit | ClusterFit | IterativeClusterFit,  Params(algorithm, weights, weigh_colour_by_alpha)
+    COLOUR_WEIGHTS_UNIFORM, COLOUR_WEIGHTS_PERCEPTUAL, num_blocks
+
+Where the reference panics (short buffers, zero width) these raise TexpressoError.  All arithmetic runs in
+the CUDA kernels of csrc/; there is no CPU path.
+"""
+import ctypes
+import enum
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ._lib import CParams, TexpressoError, check, load
+
+__all__ = ["Format", "Algorithm", "Params", "ColourWeights", "COLOUR_WEIGHTS_UNIFORM", "COLOUR_WEIGHTS_PERCEPTUAL",
+           "num_blocks", "TexpressoError", "shard_rows", "compress_multi", "compress_batch", "compress_blocks",
+           "decompress_blocks", "device_count", "set_device", "kernel_launches", "version"]
+
+ColourWeights = tuple
+COLOUR_WEIGHTS_UNIFORM = (1.0, 1.0, 1.0)                 # lib.rs:71
+COLOUR_WEIGHTS_PERCEPTUAL = (0.2126, 0.7152, 0.0722)     # lib.rs:74
+
+
+class Algorithm(enum.IntEnum):                           # lib.rs:49-59
+    RangeFit = 0
+    ClusterFit = 1
+    IterativeClusterFit = 2
+
+    @classmethod
+    def default(cls):                                    # lib.rs:61-65
+        return cls.ClusterFit
+
+
+@dataclass(frozen=True)
+class Params:                                            # lib.rs:76-100
+    algorithm: Algorithm = Algorithm.ClusterFit
+    weights: tuple = COLOUR_WEIGHTS_PERCEPTUAL
+    weigh_colour_by_alpha: bool = False
+
+    def _c(self):
+        return CParams(int(self.algorithm), (ctypes.c_float * 3)(*[float(x) for x in self.weights]),
+                       1 if self.weigh_colour_by_alpha else 0)
+
+
+def num_blocks(size):                                    # lib.rs:103-105
+    return (int(size) + 3) // 4
+
+
+def _u8(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError(f"{name} must be uint8")
+    return np.ascontiguousarray(a).reshape(-1)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Format(enum.IntEnum):                              # lib.rs:39-46
+    Bc1 = 0
+    Bc2 = 1
+    Bc3 = 2
+    Bc4 = 3
+    Bc5 = 4
+
+    def block_size(self):                                # lib.rs:159-168
+        return load().txp_block_size(int(self))
+
+    def compressed_size(self, width, height):            # lib.rs:175-179
+        return load().txp_compressed_size(int(self), width, height)
+
+    def compress(self, rgba, width, height, params=None, output=None):
+        """Format::compress (lib.rs:287-335).  `output` (uint8 array) is filled in place and returned; if
+        omitted an array of compressed_size bytes is allocated."""
+        rgba = _u8(rgba, "rgba")
+        params = params or Params()
+        if output is None:
+            output = np.empty(self.compressed_size(width, height), dtype=np.uint8)
+        out = _u8(output, "output")
+        if not np.shares_memory(out, output):
+            raise ValueError("output must be a contiguous uint8 array")
+        cp = params._c()
+        check(load().txp_compress(int(self), _ptr(rgba), rgba.size, width, height, ctypes.byref(cp), _ptr(out), out.size))
+        return output
+
+    def decompress(self, data, width, height, output=None):
+        """Format::decompress (lib.rs:124-156)."""
+        data = _u8(data, "data")
+        if output is None:
+            output = np.empty(width * height * 4, dtype=np.uint8)
+        out = _u8(output, "output")
+        if not np.shares_memory(out, output):
+            raise ValueError("output must be a contiguous uint8 array")
+        check(load().txp_decompress(int(self), _ptr(data), data.size, width, height, _ptr(out), out.size))
+        return output
+
+    def compress_block_masked(self, rgba, mask, params=None, output=None):
+        """Format::compress_block_masked (lib.rs:188-234): rgba is 16x4 bytes, mask bit i = pixel i valid."""
+        rgba = _u8(rgba, "rgba")
+        if rgba.size != 64:
+            raise ValueError("rgba must hold 16 RGBA pixels")
+        params = params or Params()
+        if output is None:
+            output = np.empty(self.block_size(), dtype=np.uint8)
+        out = _u8(output, "output")
+        cp = params._c()
+        check(load().txp_compress_block_masked(int(self), _ptr(rgba), int(mask) & 0xFFFFFFFF, ctypes.byref(cp), _ptr(out), out.size))
+        return output
+
+    def decompress_block(self, block):
+        """Format::decompress_block (lib.rs:240-277) -> (16, 4) uint8."""
+        block = _u8(block, "block")
+        out = np.empty(64, dtype=np.uint8)
+        check(load().txp_decompress_block(int(self), _ptr(block), block.size, _ptr(out)))
+        return out.reshape(16, 4)
+
+
+# ---- extensions beyond the reference surface (sharding / batching / bulk block calls) -------------------
+def compress_blocks(fmt, rgba_blocks, masks, params=None):
+    """n independent compress_block_masked calls in one launch: rgba_blocks (n,64) uint8, masks (n,) uint32."""
+    rgba_blocks = _u8(rgba_blocks, "rgba_blocks")
+    masks = np.ascontiguousarray(masks, dtype=np.uint32).reshape(-1)
+    n = masks.size
+    if rgba_blocks.size != 64 * n:
+        raise ValueError("rgba_blocks must be n x 64 bytes")
+    params = params or Params()
+    out = np.empty(n * Format(fmt).block_size(), dtype=np.uint8)
+    cp = params._c()
+    check(load().txp_compress_blocks(int(fmt), _ptr(rgba_blocks), _ptr(masks), n, ctypes.byref(cp), _ptr(out)))
+    return out.reshape(n, -1)
+
+
+def decompress_blocks(fmt, blocks):
+    blocks = _u8(blocks, "blocks")
+    bs = Format(fmt).block_size()
+    n = blocks.size // bs
+    out = np.empty(n * 64, dtype=np.uint8)
+    check(load().txp_decompress_blocks(int(fmt), _ptr(blocks), n, _ptr(out)))
+    return out.reshape(n, 16, 4)
+
+
+def shard_rows(height, rank, world):
+    """Block-row range [begin, end) owned by `rank` of `world` (reference grain: one block row, lib.rs:300-305)."""
+    a, b = ctypes.c_size_t(), ctypes.c_size_t()
+    load().txp_shard_rows(height, rank, world, ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def compress_multi(fmt, rgba, width, height, params=None, n_gpus=1, output=None):
+    rgba = _u8(rgba, "rgba")
+    params = params or Params()
+    if output is None:
+        output = np.empty(Format(fmt).compressed_size(width, height), dtype=np.uint8)
+    out = _u8(output, "output")
+    cp = params._c()
+    check(load().txp_compress_multi(int(fmt), _ptr(rgba), rgba.size, width, height, ctypes.byref(cp), _ptr(out), out.size, n_gpus))
+    return output
+
+
+def compress_batch(fmt, textures, params=None, n_gpus=1):
+    """textures: list of (rgba uint8 array, width, height); texture t is encoded on device t % n_gpus."""
+    params = params or Params()
+    n = len(textures)
+    arrs = [_u8(t[0], "rgba") for t in textures]
+    outs = [np.empty(Format(fmt).compressed_size(t[1], t[2]), dtype=np.uint8) for t in textures]
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    ins = (vp * n)(*[a.ctypes.data for a in arrs])
+    ous = (vp * n)(*[o.ctypes.data for o in outs])
+    ws = (sz * n)(*[t[1] for t in textures])
+    hs = (sz * n)(*[t[2] for t in textures])
+    cp = params._c()
+    check(load().txp_compress_batch(int(fmt), ins, ws, hs, n, ctypes.byref(cp), ous, n_gpus))
+    return outs
+
+
+def device_count():
+    n = load().txp_device_count()
+    if n < 0:
+        check(n)
+    return n
+
+
+def set_device(device):
+    check(load().txp_set_device(device))
+
+
+def kernel_launches():
+    return load().txp_kernel_launches()
+
+
+def version():
+    return load().txp_version().decode()

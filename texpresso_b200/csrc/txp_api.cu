@@ -1,0 +1,569 @@
+// txp_api.cu -- C ABI (include/texpresso_b200.h) over the sm_100a kernels.
+//
+// Host side of the drop-in boundary: argument checks that mirror the reference's panics
+// (lib.rs:295, :138, :324), per-device contexts (streams, pinned staging, device scratch), a chunked
+// H2D -> kernel -> D2H pipeline for host buffers, block-row sharding across devices.  No CPU fallback:
+// every data path ends in a kernel launch or an error code.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/texpresso_b200.h"
+#include "single_lut_data.h"
+#include "txp_common.cuh"
+#include "txp_alpha.cuh"
+#include "txp_colour.cuh"
+#include "txp_decode.cuh"
+
+namespace txp {
+
+// ---------------------------------------------------------------------------------------------------
+// BC1/BC2/BC3 encoder kernel: one warp per block (see txp_colour.cuh)
+// ---------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(COLOUR_WARPS * 32) colour_encode_kernel(const BlockSource src, const EncodeParams prm,
+                                                                          uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* tab4 = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* tab3 = tab4 + TAB4_PAD;
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem + (TAB4_PAD + TAB3_PAD) * 4);
+    if (prm.algorithm != RANGE_FIT) {
+        for (int i = threadIdx.x; i < TAB4_N; i += blockDim.x) tab4[i] = g_tab4[i];
+        for (int i = threadIdx.x; i < TAB3_N; i += blockDim.x) tab3[i] = g_tab3[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t b = (uint64_t)blockIdx.x * COLOUR_WARPS + warp;
+    if (b >= src.nblocks) return;
+
+    // gather the 4x4 block: lanes 0..15 <-> pixels (lib.rs:311-330)
+    uint32_t pix = 0;
+    bool valid = false;
+    if (lane < 16) {
+        if (src.masks) {
+            pix = __ldg(reinterpret_cast<const uint32_t*>(src.rgba) + b * 16 + lane);
+            valid = (__ldg(src.masks + b) >> lane) & 1u;
+        } else {
+            const uint32_t bx = (uint32_t)(b % src.bw), by = (uint32_t)(b / src.bw);
+            const uint32_t sx = 4 * bx + (lane & 3), sy = 4 * by + (lane >> 2);
+            valid = sx < src.w && sy < src.h;
+            if (valid) pix = __ldg(reinterpret_cast<const uint32_t*>(src.rgba) + (size_t)sy * src.w + sx);
+        }
+    }
+    uint2 alpha_half = make_uint2(0u, 0u);
+    if (FMT == BC2) alpha_half = warp_alpha_bc2(pix >> 24, valid, lane);          // lib.rs:198
+    if (FMT == BC3) alpha_half = warp_alpha_bc3(pix >> 24, valid, lane);          // lib.rs:199
+    const uint2 colour = colour_block<FMT == BC1>(pix, valid, prm, scratch + warp, tab3, tab4, lane);
+    if (lane == 0) {
+        if (FMT == BC1) reinterpret_cast<uint2*>(out)[b] = colour;
+        else reinterpret_cast<uint4*>(out)[b] = make_uint4(alpha_half.x, alpha_half.y, colour.x, colour.y);   // lib.rs:213
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host runtime
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string t_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
+
+#define TXP_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            return fail(TXP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+        }                                                                                       \
+    } while (0)
+
+constexpr int MAX_DEVICES = 64;
+constexpr int NSLOTS = 3;
+constexpr size_t CHUNK_BYTES = 32u << 20;   // input bytes per pipeline stage
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    size_t h_in_cap = 0, h_out_cap = 0, d_in_cap = 0, d_out_cap = 0;
+    // deferred copy of a staged result into a pageable caller buffer
+    uint8_t* user_out = nullptr;
+    size_t user_out_bytes = 0;
+    bool busy = false;
+};
+
+struct DeviceCtx {
+    std::mutex mu;
+    bool ready = false;
+    Slot slots[NSLOTS];
+    uint32_t* d_masks = nullptr;
+    size_t masks_cap = 0;
+};
+
+static DeviceCtx g_ctx[MAX_DEVICES];
+
+static void build_tables(std::vector<uint32_t>& t4, std::vector<uint32_t>& t3) {
+    // 4-colour: reference loop nest cluster.rs:309-318 flattened k-major so that the candidates valid for
+    // `count` points are a prefix; entry = i<<18 | (17i+j)<<9 | (17j+k) (also the loop-order tie key).
+    t4.clear(); t3.clear();
+    for (uint32_t k = 1; k <= 16; ++k)
+        for (uint32_t j = 0; j <= k; ++j)
+            for (uint32_t i = 0; i <= j && i <= 15; ++i)
+                t4.push_back((i << 18) | ((17 * i + j) << 9) | (17 * j + k));
+    // 3-colour: cluster.rs:182-187, j-major
+    for (uint32_t j = 1; j <= 16; ++j)
+        for (uint32_t i = 0; i <= j && i <= 15; ++i)
+            t3.push_back((i << 9) | (17 * i + j));
+}
+
+static int ensure_ctx(int dev, DeviceCtx** out) {
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(TXP_ERR_CUDA, "device index out of range");
+    DeviceCtx& c = g_ctx[dev];
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.ready) {
+        std::vector<uint32_t> t4, t3;
+        build_tables(t4, t3);
+        if (t4.size() != TAB4_N || t3.size() != TAB3_N) return fail(TXP_ERR_CUDA, "internal: candidate table size");
+        t4.resize(TAB4_PAD, 0xFFFFFFFFu); t3.resize(TAB3_PAD, 0xFFFFFFFFu);
+        static const uint8_t lut[TXP_SINGLE_LUT_BYTES] = TXP_SINGLE_LUT_INIT;
+        TXP_CUDA(cudaMemcpyToSymbol(g_tab4, t4.data(), TAB4_PAD * 4));
+        TXP_CUDA(cudaMemcpyToSymbol(g_tab3, t3.data(), TAB3_PAD * 4));
+        TXP_CUDA(cudaMemcpyToSymbol(c_single_lut, lut, sizeof lut));
+        TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
+        TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
+        TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
+        for (Slot& s : c.slots) {
+            TXP_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            TXP_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        c.ready = true;
+    }
+    *out = &c;
+    return TXP_OK;
+}
+
+static int current_ctx(DeviceCtx** out, int* dev_out = nullptr) {
+    int dev = 0;
+    TXP_CUDA(cudaGetDevice(&dev));
+    if (dev_out) *dev_out = dev;
+    return ensure_ctx(dev, out);
+}
+
+static int grow_dev(uint8_t** p, size_t* cap, size_t need) {
+    if (*cap >= need) return TXP_OK;
+    if (*p) TXP_CUDA(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    need = (need + 255) & ~size_t(255);
+    TXP_CUDA(cudaMalloc(reinterpret_cast<void**>(p), need));
+    *cap = need;
+    return TXP_OK;
+}
+
+static int grow_pinned(uint8_t** p, size_t* cap, size_t need) {
+    if (*cap >= need) return TXP_OK;
+    if (*p) TXP_CUDA(cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    TXP_CUDA(cudaHostAlloc(reinterpret_cast<void**>(p), need, cudaHostAllocDefault));
+    *cap = need;
+    return TXP_OK;
+}
+
+// true if the driver can DMA from/to this pointer directly (pinned / registered host, device, managed)
+static bool dma_direct(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type != cudaMemoryTypeUnregistered;
+}
+
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice;
+}
+
+static int check_params(int format, const txp_params* p) {
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if (!p) return fail(TXP_ERR_ARGUMENT, "params is null");
+    if (p->algorithm > 2) return fail(TXP_ERR_FORMAT, "algorithm must be 0..2");
+    return TXP_OK;
+}
+
+static EncodeParams to_device_params(const txp_params* p) {
+    EncodeParams e;
+    e.algorithm = (int)p->algorithm;
+    e.wx = p->weights[0]; e.wy = p->weights[1]; e.wz = p->weights[2];
+    e.alpha_weighted = p->weigh_colour_by_alpha ? 1 : 0;
+    return e;
+}
+
+// ---- kernel launchers -------------------------------------------------------------------------------
+static int launch_encode(int format, const BlockSource& src, const txp_params* p, uint8_t* d_out, cudaStream_t st) {
+    if (src.nblocks == 0) return TXP_OK;
+    if (src.nblocks > 0x7FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^31-1 blocks in one launch");
+    const EncodeParams e = to_device_params(p);
+    if (format == BC4 || format == BC5) {
+        const unsigned grid = (unsigned)((src.nblocks + 255) / 256);
+        if (format == BC4) alpha_encode_kernel<BC4><<<grid, 256, 0, st>>>(src, d_out);
+        else alpha_encode_kernel<BC5><<<grid, 256, 0, st>>>(src, d_out);
+    } else {
+        const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
+        const unsigned threads = COLOUR_WARPS * 32;
+        if (format == BC1) colour_encode_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
+        else if (format == BC2) colour_encode_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
+        else colour_encode_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    TXP_CUDA(cudaGetLastError());
+    return TXP_OK;
+}
+
+static int launch_decode(int format, const uint8_t* d_data, uint64_t nblocks, uint32_t w, uint32_t h, uint32_t bw,
+                         uint8_t* d_out, cudaStream_t st) {
+    if (nblocks == 0) return TXP_OK;
+    if (nblocks > 0x7FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^31-1 blocks in one launch");
+    const unsigned grid = (unsigned)((nblocks + 255) / 256);
+    const int vec_ok = (w != 0 && (w % 4) == 0 && (reinterpret_cast<uintptr_t>(d_out) % 16) == 0) ? 1 : 0;
+    switch (format) {
+    case BC1: decode_kernel<BC1><<<grid, 256, 0, st>>>(d_data, nblocks, w, h, bw, vec_ok, d_out); break;
+    case BC2: decode_kernel<BC2><<<grid, 256, 0, st>>>(d_data, nblocks, w, h, bw, vec_ok, d_out); break;
+    case BC3: decode_kernel<BC3><<<grid, 256, 0, st>>>(d_data, nblocks, w, h, bw, vec_ok, d_out); break;
+    case BC4: decode_kernel<BC4><<<grid, 256, 0, st>>>(d_data, nblocks, w, h, bw, vec_ok, d_out); break;
+    default:  decode_kernel<BC5><<<grid, 256, 0, st>>>(d_data, nblocks, w, h, bw, vec_ok, d_out); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    TXP_CUDA(cudaGetLastError());
+    return TXP_OK;
+}
+
+static BlockSource image_source(const uint8_t* d_rgba, size_t w, size_t h, uint64_t nblocks) {
+    BlockSource s;
+    s.rgba = d_rgba; s.masks = nullptr;
+    s.w = (uint32_t)w; s.h = (uint32_t)h; s.bw = (uint32_t)((w + 3) / 4);
+    s.nblocks = nblocks;
+    s.vec_ok = ((w % 4) == 0 && (reinterpret_cast<uintptr_t>(d_rgba) % 16) == 0) ? 1 : 0;
+    return s;
+}
+
+static int check_dims(size_t w, size_t h) {
+    if (w == 0) return fail(TXP_ERR_DIMENSIONS, "width must be non-zero");
+    if (w > 0x3FFFFFFFull || h > 0x3FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "dimension too large");
+    return TXP_OK;
+}
+
+// ---- slot helpers -------------------------------------------------------------------------------------
+static int slot_wait(Slot& s) {
+    if (!s.busy) return TXP_OK;
+    TXP_CUDA(cudaEventSynchronize(s.done));
+    if (s.user_out) { std::memcpy(s.user_out, s.h_out, s.user_out_bytes); s.user_out = nullptr; }
+    s.busy = false;
+    return TXP_OK;
+}
+
+// Encode block rows [row0,row1) (clipped to nblocks_total) of an image held in HOST memory on the
+// current device.  `out` points at the first byte of block row `row0`.
+static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p,
+                              uint8_t* out, size_t row0, size_t row1, uint64_t blocks_in_range) {
+    const size_t bs = (size_t)block_bytes(format), bw = (w + 3) / 4;
+    const bool in_direct = dma_direct(rgba), out_direct = dma_direct(out);
+    size_t rows_per_chunk = CHUNK_BYTES / (16 * w);
+    if (rows_per_chunk == 0) rows_per_chunk = 1;
+    int rc = TXP_OK;
+    size_t chunk = 0;
+    uint64_t blocks_left = blocks_in_range;
+    for (size_t r = row0; r < row1 && blocks_left > 0 && rc == TXP_OK; r += rows_per_chunk, ++chunk) {
+        const size_t r_end = (r + rows_per_chunk < row1) ? r + rows_per_chunk : row1;
+        uint64_t nblk = (uint64_t)(r_end - r) * bw;
+        if (nblk > blocks_left) nblk = blocks_left;
+        blocks_left -= nblk;
+        Slot& s = c.slots[chunk % NSLOTS];
+        if ((rc = slot_wait(s)) != TXP_OK) break;
+        // pixel rows of this chunk that exist in the image (rows past h are fully masked)
+        const size_t y0 = 4 * r, y1 = (4 * r_end < h) ? 4 * r_end : h;
+        const size_t h_sub = y1 > y0 ? y1 - y0 : 0;
+        const size_t in_bytes = h_sub * w * 4, out_bytes = (size_t)nblk * bs;
+        if ((rc = grow_dev(&s.d_in, &s.d_in_cap, in_bytes ? in_bytes : 16)) != TXP_OK) break;
+        if ((rc = grow_dev(&s.d_out, &s.d_out_cap, out_bytes)) != TXP_OK) break;
+        if (in_bytes) {
+            const uint8_t* src_ptr = rgba + y0 * w * 4;
+            if (!in_direct) {
+                if ((rc = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) break;
+                std::memcpy(s.h_in, src_ptr, in_bytes);
+                src_ptr = s.h_in;
+            }
+            TXP_CUDA(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
+        }
+        const BlockSource bsrc = image_source(s.d_in, w, h_sub, nblk);
+        if ((rc = launch_encode(format, bsrc, p, s.d_out, s.stream)) != TXP_OK) break;
+        uint8_t* dst = out + (r - row0) * bw * bs;
+        if (out_direct) {
+            TXP_CUDA(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
+        } else {
+            if ((rc = grow_pinned(&s.h_out, &s.h_out_cap, out_bytes)) != TXP_OK) break;
+            TXP_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+            s.user_out = dst; s.user_out_bytes = out_bytes;
+        }
+        TXP_CUDA(cudaEventRecord(s.done, s.stream));
+        s.busy = true;
+    }
+    for (Slot& s : c.slots) { const int r2 = slot_wait(s); if (rc == TXP_OK) rc = r2; }
+    return rc;
+}
+
+static int compress_checked(int format, const uint8_t* rgba, size_t rgba_len, size_t w, size_t h, const txp_params* p,
+                            const uint8_t* output, size_t output_len) {
+    int rc;
+    if ((rc = check_params(format, p)) != TXP_OK) return rc;
+    if ((rc = check_dims(w, h)) != TXP_OK) return rc;
+    if (!rgba && w * h) return fail(TXP_ERR_ARGUMENT, "rgba is null");
+    if (!output) return fail(TXP_ERR_ARGUMENT, "output is null");
+    if (rgba_len < w * h * 4) return fail(TXP_ERR_BUFFER_TOO_SMALL, "rgba shorter than 4*width*height");
+    const size_t need = txp_compressed_size(format, w, h);
+    if (output_len < need) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than compressed_size (reference asserts, lib.rs:295)");
+    if (output_len % (size_t)block_bytes(format)) return fail(TXP_ERR_ARGUMENT, "output_len is not a whole number of blocks");
+    return TXP_OK;
+}
+
+}  // namespace txp
+
+using namespace txp;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+size_t txp_num_blocks(size_t size) { return (size + 3) / 4; }
+
+size_t txp_block_size(int format) { return (format < 0 || format > 4) ? 0 : (size_t)block_bytes(format); }
+
+size_t txp_compressed_size(int format, size_t width, size_t height) {
+    return txp_num_blocks(width) * txp_num_blocks(height) * txp_block_size(format);
+}
+
+const char* txp_last_error(void) { return t_last_error.c_str(); }
+uint64_t txp_kernel_launches(void) { return g_launches.load(); }
+const char* txp_version(void) { return "texpresso_b200 0.1 (sm_100a)"; }
+
+int txp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail(TXP_ERR_CUDA, "no CUDA device"); }
+    return n;
+}
+
+int txp_set_device(int device) {
+    TXP_CUDA(cudaSetDevice(device));
+    return TXP_OK;
+}
+
+void txp_shard_rows(size_t height, int rank, int world, size_t* row_begin, size_t* row_end) {
+    const size_t rows = (height + 3) / 4;
+    if (world < 1) world = 1;
+    if (rank < 0) rank = 0;
+    if (rank >= world) rank = world - 1;
+    if (row_begin) *row_begin = rows * (size_t)rank / (size_t)world;
+    if (row_end) *row_end = rows * (size_t)(rank + 1) / (size_t)world;
+}
+
+int txp_compress_device(int format, const void* d_rgba, size_t width, size_t height, const txp_params* params,
+                        void* d_output, size_t output_len, void* cuda_stream) {
+    int rc;
+    if ((rc = check_params(format, params)) != TXP_OK) return rc;
+    if ((rc = check_dims(width, height)) != TXP_OK) return rc;
+    if (!d_output || (!d_rgba && width * height)) return fail(TXP_ERR_ARGUMENT, "null device pointer");
+    if (output_len < txp_compressed_size(format, width, height)) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than compressed_size");
+    if (output_len % (size_t)block_bytes(format)) return fail(TXP_ERR_ARGUMENT, "output_len is not a whole number of blocks");
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    const BlockSource src = image_source(static_cast<const uint8_t*>(d_rgba), width, height, output_len / (size_t)block_bytes(format));
+    return launch_encode(format, src, params, static_cast<uint8_t*>(d_output), static_cast<cudaStream_t>(cuda_stream));
+}
+
+int txp_decompress_device(int format, const void* d_data, size_t width, size_t height, void* d_output, size_t output_len,
+                          void* cuda_stream) {
+    int rc;
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if ((rc = check_dims(width, height)) != TXP_OK) return rc;
+    if (!d_data || !d_output) return fail(TXP_ERR_ARGUMENT, "null device pointer");
+    if (output_len < width * height * 4) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than 4*width*height");
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    const uint64_t nblocks = (uint64_t)txp_num_blocks(width) * txp_num_blocks(height);
+    return launch_decode(format, static_cast<const uint8_t*>(d_data), nblocks, (uint32_t)width, (uint32_t)height,
+                         (uint32_t)txp_num_blocks(width), static_cast<uint8_t*>(d_output), static_cast<cudaStream_t>(cuda_stream));
+}
+
+int txp_compress(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height, const txp_params* params,
+                 uint8_t* output, size_t output_len) {
+    int rc;
+    if ((rc = compress_checked(format, rgba, rgba_len, width, height, params, output, output_len)) != TXP_OK) return rc;
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    if (is_device_ptr(rgba) && is_device_ptr(output)) {
+        if ((rc = txp_compress_device(format, rgba, width, height, params, output, output_len, nullptr)) != TXP_OK) return rc;
+        TXP_CUDA(cudaStreamSynchronize(nullptr));
+        return TXP_OK;
+    }
+    const size_t bs = (size_t)block_bytes(format), bw = txp_num_blocks(width);
+    const uint64_t nblocks = output_len / bs;
+    const size_t rows = (size_t)((nblocks + bw - 1) / bw);
+    std::lock_guard<std::mutex> lk(c->mu);
+    return compress_host_rows(*c, format, rgba, width, height, params, output, 0, rows, nblocks);
+}
+
+int txp_decompress(int format, const uint8_t* data, size_t data_len, size_t width, size_t height, uint8_t* output,
+                   size_t output_len) {
+    int rc;
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if ((rc = check_dims(width, height)) != TXP_OK) return rc;
+    if (!data || !output) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    const size_t need_in = txp_compressed_size(format, width, height), need_out = width * height * 4;
+    if (data_len < need_in) return fail(TXP_ERR_BUFFER_TOO_SMALL, "data shorter than compressed_size (reference: slice panic, lib.rs:138)");
+    if (output_len < need_out) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than 4*width*height");
+    if (need_out == 0) return TXP_OK;
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot& s = c->slots[0];
+    if ((rc = grow_dev(&s.d_in, &s.d_in_cap, need_in)) != TXP_OK) return rc;
+    if ((rc = grow_dev(&s.d_out, &s.d_out_cap, need_out)) != TXP_OK) return rc;
+    TXP_CUDA(cudaMemcpyAsync(s.d_in, data, need_in, cudaMemcpyDefault, s.stream));
+    const uint64_t nblocks = (uint64_t)txp_num_blocks(width) * txp_num_blocks(height);
+    if ((rc = launch_decode(format, s.d_in, nblocks, (uint32_t)width, (uint32_t)height, (uint32_t)txp_num_blocks(width), s.d_out, s.stream)) != TXP_OK) return rc;
+    TXP_CUDA(cudaMemcpyAsync(output, s.d_out, need_out, cudaMemcpyDefault, s.stream));
+    TXP_CUDA(cudaStreamSynchronize(s.stream));
+    return TXP_OK;
+}
+
+int txp_compress_blocks(int format, const uint8_t* rgba_blocks, const uint32_t* masks, size_t n, const txp_params* params,
+                        uint8_t* output) {
+    int rc;
+    if ((rc = check_params(format, params)) != TXP_OK) return rc;
+    if (n == 0) return TXP_OK;
+    if (!rgba_blocks || !masks || !output) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot& s = c->slots[0];
+    const size_t bs = (size_t)block_bytes(format);
+    if ((rc = grow_dev(&s.d_in, &s.d_in_cap, n * 64)) != TXP_OK) return rc;
+    if ((rc = grow_dev(&s.d_out, &s.d_out_cap, n * bs)) != TXP_OK) return rc;
+    if (c->masks_cap < n) {
+        if (c->d_masks) TXP_CUDA(cudaFree(c->d_masks));
+        c->d_masks = nullptr; c->masks_cap = 0;
+        TXP_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_masks), n * 4));
+        c->masks_cap = n;
+    }
+    TXP_CUDA(cudaMemcpyAsync(s.d_in, rgba_blocks, n * 64, cudaMemcpyDefault, s.stream));
+    TXP_CUDA(cudaMemcpyAsync(c->d_masks, masks, n * 4, cudaMemcpyDefault, s.stream));
+    BlockSource src;
+    src.rgba = s.d_in; src.masks = c->d_masks; src.w = 0; src.h = 0; src.bw = 1; src.nblocks = n; src.vec_ok = 1;
+    if ((rc = launch_encode(format, src, params, s.d_out, s.stream)) != TXP_OK) return rc;
+    TXP_CUDA(cudaMemcpyAsync(output, s.d_out, n * bs, cudaMemcpyDefault, s.stream));
+    TXP_CUDA(cudaStreamSynchronize(s.stream));
+    return TXP_OK;
+}
+
+int txp_decompress_blocks(int format, const uint8_t* blocks, size_t n, uint8_t* rgba_blocks) {
+    int rc;
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if (n == 0) return TXP_OK;
+    if (!blocks || !rgba_blocks) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot& s = c->slots[0];
+    const size_t bs = (size_t)block_bytes(format);
+    if ((rc = grow_dev(&s.d_in, &s.d_in_cap, n * bs)) != TXP_OK) return rc;
+    if ((rc = grow_dev(&s.d_out, &s.d_out_cap, n * 64)) != TXP_OK) return rc;
+    TXP_CUDA(cudaMemcpyAsync(s.d_in, blocks, n * bs, cudaMemcpyDefault, s.stream));
+    if ((rc = launch_decode(format, s.d_in, n, 0, 0, 1, s.d_out, s.stream)) != TXP_OK) return rc;
+    TXP_CUDA(cudaMemcpyAsync(rgba_blocks, s.d_out, n * 64, cudaMemcpyDefault, s.stream));
+    TXP_CUDA(cudaStreamSynchronize(s.stream));
+    return TXP_OK;
+}
+
+int txp_compress_block_masked(int format, const uint8_t rgba[64], uint32_t mask, const txp_params* params, uint8_t* output,
+                              size_t output_len) {
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if (output_len < (size_t)block_bytes(format)) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than block_size");
+    return txp_compress_blocks(format, rgba, &mask, 1, params, output);
+}
+
+int txp_decompress_block(int format, const uint8_t* block, size_t block_len, uint8_t output[64]) {
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if (block_len < (size_t)block_bytes(format)) return fail(TXP_ERR_BUFFER_TOO_SMALL, "block shorter than block_size");
+    return txp_decompress_blocks(format, block, 1, output);
+}
+
+int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height, const txp_params* params,
+                       uint8_t* output, size_t output_len, int n_gpus) {
+    int rc;
+    if ((rc = compress_checked(format, rgba, rgba_len, width, height, params, output, output_len)) != TXP_OK) return rc;
+    const int ndev = txp_device_count();
+    if (ndev < 0) return ndev;
+    if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
+    const size_t bs = (size_t)block_bytes(format), bw = txp_num_blocks(width);
+    const uint64_t nblocks = output_len / bs;
+    const size_t rows = (size_t)((nblocks + bw - 1) / bw);
+    std::vector<int> rcs((size_t)n_gpus, TXP_OK);
+    std::vector<std::string> errs((size_t)n_gpus);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_gpus; ++g) {
+        workers.emplace_back([&, g]() {
+            const size_t r0 = rows * (size_t)g / (size_t)n_gpus, r1 = rows * (size_t)(g + 1) / (size_t)n_gpus;
+            if (r0 >= r1) return;
+            int r = TXP_OK;
+            DeviceCtx* c = nullptr;
+            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            if (r == TXP_OK) {
+                uint64_t nb = (uint64_t)(r1 - r0) * bw;
+                const uint64_t first = (uint64_t)r0 * bw;
+                if (first + nb > nblocks) nb = nblocks - first;
+                std::lock_guard<std::mutex> lk(c->mu);
+                r = compress_host_rows(*c, format, rgba, width, height, params, output + first * bs, r0, r1, nb);
+            }
+            rcs[(size_t)g] = r;
+            if (r != TXP_OK) errs[(size_t)g] = t_last_error;
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int g = 0; g < n_gpus; ++g)
+        if (rcs[(size_t)g] != TXP_OK) return fail(rcs[(size_t)g], "gpu " + std::to_string(g) + ": " + errs[(size_t)g]);
+    return TXP_OK;
+}
+
+int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* widths, const size_t* heights, size_t n_textures,
+                       const txp_params* params, uint8_t* const* outputs, int n_gpus) {
+    int rc;
+    if ((rc = check_params(format, params)) != TXP_OK) return rc;
+    if (n_textures == 0) return TXP_OK;
+    if (!rgba || !widths || !heights || !outputs) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    const int ndev = txp_device_count();
+    if (ndev < 0) return ndev;
+    if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
+    std::vector<int> rcs((size_t)n_gpus, TXP_OK);
+    std::vector<std::string> errs((size_t)n_gpus);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_gpus; ++g) {
+        workers.emplace_back([&, g]() {
+            int r = TXP_OK;
+            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus) {
+                const size_t w = widths[t], h = heights[t];
+                r = txp_compress(format, rgba[t], w * h * 4, w, h, params, outputs[t], txp_compressed_size(format, w, h));
+            }
+            rcs[(size_t)g] = r;
+            if (r != TXP_OK) errs[(size_t)g] = t_last_error;
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int g = 0; g < n_gpus; ++g)
+        if (rcs[(size_t)g] != TXP_OK) return fail(rcs[(size_t)g], "gpu " + std::to_string(g) + ": " + errs[(size_t)g]);
+    return TXP_OK;
+}
+
+}  // extern "C"
