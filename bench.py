@@ -288,7 +288,7 @@ def run_ours(args):
             threads = host_threads()
             crop = 256
             mp, dt = cpu_reference_time(crop, threads)
-            while dt < 4.0 and crop < 2048:
+            while dt < 4.0 and crop < 4096:
                 crop *= 2
                 mp, dt = cpu_reference_time(crop, threads)
             line["cpu_baseline"] = {"value": mp, "unit": UNIT, "cores": threads, "kind": "port",

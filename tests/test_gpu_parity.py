@@ -220,10 +220,10 @@ def test_fullsize_16384_bc4_bc5(T):
         y0 = 8000
         want = O.compress(fmt, img[y0:y0 + 64], w, 64, op, threads=8)
         assert np.array_equal(a[(y0 // 4) * rowbytes:(y0 // 4 + 16) * rowbytes], want)
-        # decode(encode(x)) channel error is bounded by half the largest codebook step (range/5 -> <= 26)
-        dec = T.Format(fmt).decompress(a[:rowbytes * 64], w, 256).reshape(256, w, 4)
-        err = np.abs(dec[..., 0].astype(np.int16) - img[:256, :, 0].astype(np.int16)).max()
-        assert err <= 26
+        # decoder on the same blocks == oracle decoder (a quality bound is not asserted: the reference's 7-point
+        # codebook quirk Q1 legitimately produces large errors on blocks holding both 0/255 and mid values)
+        dec = T.Format(fmt).decompress(a[:rowbytes * 64], w, 256)
+        assert np.array_equal(dec, O.decompress(fmt, a[:rowbytes * 64], w, 256))
         del a
 
 
