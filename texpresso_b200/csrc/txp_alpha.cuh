@@ -134,6 +134,93 @@ __device__ __forceinline__ uint2 alpha_fit_thread(const uint32_t v[16], const ui
     return make_uint2(a0 | (a1 << 8) | (g0 << 16), (g0 >> 16) | (g1 << 8));
 }
 
+// ---- fast path for fully valid blocks (mask == 0xFFFF) ------------------------------------------------------
+// The nearest-code search is moved from the ALU pipe (|v-c| keys) to the FMA pipe:
+//   (v-c)^2 = v^2 - 2vc + c^2, so  argmin_j ((v-c_j)^2, j)  ==  argmin_j  key_j,
+//   key_j = 8*(c_j^2 - 2*v*c_j) + j = v*(-16*c_j) + (8*c_j^2 + j)        -- one IMAD per code and pixel,
+// the same lexicographic (distance, first index) rule as alpha.rs:101-111.  key_min & 7 is the index and
+// sum(key_min - j_min) = 8*(err - sum v^2), so err5 <= err7 is decided on the key sums directly.
+struct KeyBook { int a[8], b[8]; };
+
+__device__ __forceinline__ void make_keybook(const int codes[8], KeyBook& kb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { kb.a[j] = -16 * codes[j]; kb.b[j] = 8 * codes[j] * codes[j] + j; }
+}
+
+__device__ __forceinline__ int best_key(const int v, const KeyBook& kb) {
+    int k[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k[j] = v * kb.a[j] + kb.b[j];
+    const int m0 = __vimin3_s32(k[0], k[1], k[2]);
+    const int m1 = __vimin3_s32(k[3], k[4], k[5]);
+    return __vimin3_s32(m0, m1, min(k[6], k[7]));
+}
+
+// 24-bit words of eight 3-bit fields; EVEN3 selects fields 0,2,4,6 (6-bit lanes at bits 0,6,12,18)
+constexpr uint32_t EVEN3 = 0x1C71C7u;
+
+// sum of the sixteen 3-bit fields held in two 24-bit words
+__device__ __forceinline__ int sum_fields3(const uint32_t lo, const uint32_t hi) {
+    const uint32_t t = (lo & EVEN3) + ((lo >> 3) & EVEN3) + (hi & EVEN3) + ((hi >> 3) & EVEN3);   // 4 lanes, each <= 28
+    const uint32_t u = (t & 0x03F03Fu) + ((t >> 6) & 0x03F03Fu);                                  // 2 lanes (bits 0, 12), each <= 56
+    return (int)((u & 0xFFFu) + (u >> 12));
+}
+
+// write_alpha_block7's index swap (alpha.rs:172-178) on all eight fields at once:
+// 0->1, 1->0, x->9-x  is  f -> (9 - f) & 7   (9-0 = 9 -> 1, 9-1 = 8 -> 0)
+__device__ __forceinline__ uint32_t swap7_fields(const uint32_t w) {
+    const uint32_t nine = 0x249249u;                       // 9 in every 6-bit lane
+    const uint32_t e = (nine - (w & EVEN3)) & EVEN3;
+    const uint32_t o = (nine - ((w >> 3) & EVEN3)) & EVEN3;
+    return e | (o << 3);
+}
+
+__device__ __forceinline__ uint2 alpha_fit_full(const uint32_t v[16]) {
+    // alpha.rs:194-212 on a full mask
+    uint32_t mn = __vimin3_u32(v[0], v[1], v[2]), mx = __vimax3_u32(v[0], v[1], v[2]);
+#pragma unroll
+    for (int i = 3; i < 15; i += 2) { mn = __vimin3_u32(mn, v[i], v[i + 1]); mx = __vimax3_u32(mx, v[i], v[i + 1]); }
+    mn = min(mn, v[15]); mx = max(mx, v[15]);
+    uint32_t a5 = 0xFFFFFFFFu;            // min over (v-1) with 0 -> 0xFFFFFFFF, i.e. zeros ignored
+    int b5 = (int)0x80000000;             // max over v + 0x7FFFFF01 with 255 -> INT_MIN, i.e. 255 ignored
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        a5 = __viaddmin_u32(v[i], 0xFFFFFFFFu, a5);
+        b5 = __viaddmax_s32((int)v[i], 0x7FFFFF01, b5);
+    }
+    int min7 = (int)mn, max7 = (int)mx;
+    int min5 = a5 == 0xFFFFFFFFu ? 255 : (int)(a5 + 1u);
+    int max5 = b5 == (int)0x80000000 ? 0 : b5 - 0x7FFFFF01;
+    if (min5 > max5) min5 = max5;
+    fix_range(min5, max5, 5);
+    fix_range(min7, max7, 7);
+    int codes5[8], codes7[8];
+    alpha_codebooks(min5, max5, min7, max7, codes5, codes7);
+    KeyBook k5, k7;
+    make_keybook(codes5, k5);
+    make_keybook(codes7, k7);
+    int s5 = 0, s7 = 0;                                   // sums of the winning keys
+    uint32_t w5lo = 0, w5hi = 0, w7lo = 0, w7hi = 0;      // 3-bit indices, 8 per word
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int q5 = best_key((int)v[i], k5), q7 = best_key((int)v[i], k7);
+        s5 += q5; s7 += q7;
+        const uint32_t sh = 1u << (3 * (i & 7));
+        if (i < 8) { w5lo += ((uint32_t)q5 & 7u) * sh; w7lo += ((uint32_t)q7 & 7u) * sh; }
+        else       { w5hi += ((uint32_t)q5 & 7u) * sh; w7hi += ((uint32_t)q7 & 7u) * sh; }
+    }
+    const int e5 = s5 - sum_fields3(w5lo, w5hi), e7 = s7 - sum_fields3(w7lo, w7hi);   // 8*(err - sum v^2)
+    uint32_t a0, a1, g0, g1;
+    if (e5 <= e7) {                                       // alpha.rs:251
+        a0 = (uint32_t)min5; a1 = (uint32_t)max5; g0 = w5lo; g1 = w5hi;                // no swap: min5 <= max5 (Q3b)
+    } else {
+        // write_alpha_block7 always swaps after fix_range (Q3b)
+        a0 = (uint32_t)max7; a1 = (uint32_t)min7;
+        g0 = swap7_fields(w7lo); g1 = swap7_fields(w7hi);
+    }
+    return make_uint2(a0 | (a1 << 8) | (g0 << 16), (g0 >> 16) | (g1 << 8));
+}
+
 // ---- BC4 / BC5 encoder: one thread per block ---------------------------------------------------------
 // Loads: 4 x 16-byte row segments per thread; consecutive threads read consecutive 16 B, so every warp
 // load instruction covers 512 contiguous bytes per image row (fully coalesced without staging).
@@ -174,13 +261,14 @@ __global__ void __launch_bounds__(256) alpha_encode_kernel(const BlockSource src
     uint32_t v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = px[i] & 255u;    // channel 0 (lib.rs:200, :202)
-    const uint2 r0 = alpha_fit_thread(v, mask);
+    const bool full = mask == 0xFFFFu;                    // all blocks except image edges
+    const uint2 r0 = full ? alpha_fit_full(v) : alpha_fit_thread(v, mask);
     if (FMT == BC4) {
         reinterpret_cast<uint2*>(out)[b] = r0;
     } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = (px[i] >> 8) & 255u;   // channel 1 (lib.rs:203)
-        const uint2 r1 = alpha_fit_thread(v, mask);
+        const uint2 r1 = full ? alpha_fit_full(v) : alpha_fit_thread(v, mask);
         reinterpret_cast<uint4*>(out)[b] = make_uint4(r0.x, r0.y, r1.x, r1.y);
     }
 }

@@ -28,14 +28,9 @@ template <int FMT>
 __global__ void __launch_bounds__(COLOUR_WARPS * 32) colour_encode_kernel(const BlockSource src, const EncodeParams prm,
                                                                           uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t* tab4 = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* tab3 = tab4 + TAB4_PAD;
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem + (TAB4_PAD + TAB3_PAD) * 4);
-    if (prm.algorithm != RANGE_FIT) {
-        for (int i = threadIdx.x; i < TAB4_N; i += blockDim.x) tab4[i] = g_tab4[i];
-        for (int i = threadIdx.x; i < TAB3_N; i += blockDim.x) tab3[i] = g_tab3[i];
-    }
-    __syncthreads();
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem);
+    const uint32_t* tab4 = g_tab4;                          // candidate lists are read through L1 (coalesced 128 B per step)
+    const uint32_t* tab3 = g_tab3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t b = (uint64_t)blockIdx.x * COLOUR_WARPS + warp;
     if (b >= src.nblocks) return;

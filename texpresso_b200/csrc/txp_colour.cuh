@@ -44,7 +44,7 @@ struct __align__(16) WarpScratch {
     unsigned long long seen[8];
 };
 
-constexpr size_t COLOUR_SMEM = (TAB4_PAD + TAB3_PAD) * 4 + COLOUR_WARPS * sizeof(WarpScratch);
+constexpr size_t COLOUR_SMEM = COLOUR_WARPS * sizeof(WarpScratch);
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(add(a.x, b.x), add(a.y, b.y), add(a.z, b.z), add(a.w, b.w)); }
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(sub(a.x, b.x), sub(a.y, b.y), sub(a.z, b.z), sub(a.w, b.w)); }
@@ -145,6 +145,8 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
     int best_iteration = 0;
     uint32_t best_E = 0;
     unsigned long long best_ow = 0;
+    int best_rank = 0;
+    bool best_degenerate = false;
     float bka[3] = {0, 0, 0}, bkb[3] = {0, 0, 0};
     float bsx = 0, bsy = 0, bsz = 0, bex = 0, bey = 0, bez = 0;
     float axx = principle.x, axy = principle.y, axz = principle.z;
@@ -200,7 +202,7 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
         float lbest = __int_as_float(0x7F800000);
         uint32_t lE = 0xFFFFFFFFu;
         for (int c = lane; c < ncand; c += 32) {
-            const uint32_t E = tab[c];
+            const uint32_t E = __ldg(tab + c);
             const float err = THREE ? eval3(ws->S, E, xsum, prm.wx, prm.wy, prm.wz, nullptr, false)
                                     : eval4(ws->S, E, xsum, prm.wx, prm.wy, prm.wz, nullptr, false);
             if (err < lbest || (err == lbest && E < lE)) { lbest = err; lE = E; }
@@ -219,6 +221,8 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
             best_iteration = it;
             best_E = Ewin;
             best_ow = ow;
+            best_rank = rank;
+            best_degenerate = __any_sync(FULL, lane < count && sk == 0x7FFFFFFF);
 #pragma unroll
             for (int c = 0; c < 3; ++c) { bka[c] = sol.ka[c]; bkb[c] = sol.kb[c]; }
             bsx = sol.ax; bsy = sol.ay; bsz = sol.az; bex = sol.bx; bey = sol.by; bez = sol.bz;
@@ -232,15 +236,22 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
         int bi, bj, bk;
         if (THREE) { bi = (int)(best_E >> 9); bj = (int)(best_E & 511u) - 17 * bi; bk = count; }
         else { bi = (int)(best_E >> 18); bj = (int)((best_E >> 9) & 511u) - 17 * bi; bk = (int)(best_E & 511u) - 17 * bj; }
-        // unordered[order[m]] = code(m), later m overwrite earlier ones (matters only for degenerate
-        // orderings with repeated entries)
+        // unordered[order[m]] = code(m) (cluster.rs:254-262 / :396-405).  With finite keys the ordering is a
+        // permutation and point `lane` sits at position best_rank; with NaN/inf keys entries repeat and later m
+        // overwrite earlier ones, which needs the sequential form.
         int code = 0;
-        for (int m = 0; m < count; ++m) {
-            const int q = (int)((best_ow >> (4 * m)) & 15ull);
-            int cm;
-            if (THREE) cm = m < bi ? 0 : (m < bj ? 2 : 1);
-            else cm = m < bi ? 0 : (m < bj ? 2 : (m < bk ? 3 : 1));
-            if (q == lane) code = cm;
+        if (!best_degenerate) {
+            const int m = best_rank;
+            if (THREE) code = m < bi ? 0 : (m < bj ? 2 : 1);
+            else code = m < bi ? 0 : (m < bj ? 2 : (m < bk ? 3 : 1));
+        } else {
+            for (int m = 0; m < count; ++m) {
+                const int q = (int)((best_ow >> (4 * m)) & 15ull);
+                int cm;
+                if (THREE) cm = m < bi ? 0 : (m < bj ? 2 : 1);
+                else cm = m < bi ? 0 : (m < bj ? 2 : (m < bk ? 3 : 1));
+                if (q == lane) code = cm;
+            }
         }
         const uint32_t idx2 = pixel_indices(s, code, lane);
         // pack_565 of k*gridrcp is k itself (checked in tests/test_identities.py)
