@@ -191,6 +191,7 @@ static EncodeParams to_device_params(const txp_params* p) {
     e.algorithm = (int)p->algorithm;
     e.wx = p->weights[0]; e.wy = p->weights[1]; e.wz = p->weights[2];
     e.alpha_weighted = p->weigh_colour_by_alpha ? 1 : 0;
+    e.negzero2 = 0x8000000080000000ull;
     return e;
 }
 

@@ -115,6 +115,62 @@ __device__ __forceinline__ float eval4(const float4* S, const uint32_t E, const 
     return want ? solve<true>(alphax, betax, ab, wx, wy, wz, out) : solve<false>(alphax, betax, ab, wx, wy, wz, out);
 }
 
+// eval4 with the x/y lanes (and the z/w lanes of the sums) carried as fp32x2 pairs.  Same operations, same
+// association and rounding as eval4 -- only the issue slots are shared (error value is bit-identical).
+__device__ __forceinline__ float eval4_packed(const float4* S, const uint32_t E, const f32x2 xs_xy, const f32x2 xs_zw,
+                                              const float wx, const float wy, const float wz, const f32x2 nz) {
+    const float c13 = 1.0f / 3.0f, c19 = 1.0f / 9.0f, c23 = 2.0f / 3.0f, c49 = 4.0f / 9.0f, c29 = 2.0f / 9.0f;
+    const float4 p0 = S[E >> 18];                // S[0][i]
+    const float4 p1 = S[(E >> 9) & 511u];        // S[i][j]
+    const float4 p2 = S[E & 511u];               // S[j][k]
+    const f32x2 p0xy = pk(p0.x, p0.y), p0zw = pk(p0.z, p0.w);
+    const f32x2 p1xy = pk(p1.x, p1.y), p1zw = pk(p1.z, p1.w);
+    const f32x2 p2xy = pk(p2.x, p2.y), p2zw = pk(p2.z, p2.w);
+    const f32x2 p3xy = sub2(sub2(sub2(xs_xy, p2xy), p1xy), p0xy);                    // cluster.rs:320
+    const f32x2 p3zw = sub2(sub2(sub2(xs_zw, p2zw), p1zw), p0zw);
+    const f32x2 k13xy = pk(c13, c13), k13zw = pk(c13, c19), k23xy = pk(c23, c23), k23zw = pk(c23, c49);
+    const f32x2 axy = add2(mul2c(p2xy, k13xy, nz), add2(mul2c(p1xy, k23xy, nz), p0xy)); // :323-324
+    const f32x2 azw = add2(mul2c(p2zw, k13zw, nz), add2(mul2c(p1zw, k23zw, nz), p0zw));
+    const f32x2 bxy = add2(mul2c(p1xy, k13xy, nz), add2(mul2c(p2xy, k23xy, nz), p3xy)); // :327-328
+    const f32x2 bzw = add2(mul2c(p1zw, k13zw, nz), add2(mul2c(p2zw, k23zw, nz), p3zw));
+    float az, alpha2, bz, beta2;
+    upk(azw, az, alpha2);
+    upk(bzw, bz, beta2);
+    const float ab = mul(c29, add(p1.w, p2.w));                                      // :331
+    const float factor = rcp(sub(mul(alpha2, beta2), mul(ab, ab)));                  // :334-335
+    float nax, nay, nbx, nby;                                                        // :336-337
+    upk(sub2(mul2s(axy, beta2), mul2s(bxy, ab)), nax, nay);
+    upk(sub2(mul2s(bxy, alpha2), mul2s(axy, ab)), nbx, nby);
+    const float cax = clamp01(mul(nax, factor)), cay = clamp01(mul(nay, factor));    // :340-341
+    const float cbx = clamp01(mul(nbx, factor)), cby = clamp01(mul(nby, factor));
+    const float caz = clamp01(mul(sub(mul(az, beta2), mul(bz, ab)), factor));
+    const float cbz = clamp01(mul(sub(mul(bz, alpha2), mul(az, ab)), factor));
+    // grid snap :342-343  (x,y) pairs use (31,63); the z values of a and b share one pair
+    const f32x2 gxy = pk(31.0f, 63.0f), grxy = pk(1.0f / 31.0f, 1.0f / 63.0f), hh = pk(0.5f, 0.5f);
+    const f32x2 g31 = pk(31.0f, 31.0f), gr31 = pk(1.0f / 31.0f, 1.0f / 31.0f);
+    float t0, t1;
+    upk(add2(mul2c(pk(cax, cay), gxy, nz), hh), t0, t1);
+    const f32x2 a2 = mul2m(pk(truncf(t0), truncf(t1)), grxy);                        // feeds multiplies only
+    upk(add2(mul2c(pk(cbx, cby), gxy, nz), hh), t0, t1);
+    const f32x2 b2 = mul2m(pk(truncf(t0), truncf(t1)), grxy);
+    upk(add2(mul2c(pk(caz, cbz), g31, nz), hh), t0, t1);
+    float qaz, qbz;
+    upk(mul2m(pk(truncf(t0), truncf(t1)), gr31), qaz, qbz);
+    // error terms :346-353, x/y packed
+    const f32x2 e1 = add2(mul2s(mul2m(a2, a2), alpha2), mul2s(mul2m(b2, b2), beta2));
+    const f32x2 e2 = sub2(mul2s(mul2m(a2, b2), ab), mul2s(a2, axy));
+    const f32x2 e3 = sub2(e2, mul2s(b2, bxy));
+    const f32x2 e4 = fma2(pk(2.0f, 2.0f), e3, e1);        // 2*e3 exact -> same as (2*e3)+e1
+    float e5x, e5y;
+    upk(mul2c(e4, pk(wx, wy), nz), e5x, e5y);
+    // z scalar
+    const float e1z = add(mul(mul(qaz, qaz), alpha2), mul(mul(qbz, qbz), beta2));
+    const float e2z = sub(mul(mul(qaz, qbz), ab), mul(qaz, az));
+    const float e3z = sub(e2z, mul(qbz, bz));
+    const float e5z = mul(__fmaf_rn(2.0f, e3z, e1z), wz);
+    return add(add(e5x, e5y), e5z);
+}
+
 // The per-block state every fit needs.
 struct SetInfo {
     int count;               // distinct colours (uniform)
@@ -135,8 +191,8 @@ __device__ __forceinline__ uint32_t pixel_indices(const SetInfo& s, const int po
 // ---------------------------------------------------------------------------------------------------
 // ClusterFit pass (cluster.rs:152-274 for THREE, :276-417 otherwise).  Updates best_error/best_block.
 // ---------------------------------------------------------------------------------------------------
-template <bool THREE>
-__device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const int niter, const float3 principle,
+template <bool THREE, bool ITERATE>
+__device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const float3 principle,
                              WarpScratch* ws, const uint32_t* tab, const int lane,
                              float& best_error, uint2& best_block) {
     const int count = s.count;
@@ -151,6 +207,8 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
     float bsx = 0, bsy = 0, bsz = 0, bex = 0, bey = 0, bez = 0;
     float axx = principle.x, axy = principle.y, axz = principle.z;
 
+    constexpr int niter = ITERATE ? 8 : 1;                // cluster.rs:33, :59
+#pragma unroll 1
     for (int it = 0; it < niter; ++it) {
         // ---- construct_ordering (cluster.rs:78-136) ------------------------------------------------
         const float dp = lane < count ? add(add(mul(s.px, axx), mul(s.py, axy)), mul(s.pz, axz)) : FLT_MAX;
@@ -175,11 +233,13 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
         lo = __reduce_or_sync(FULL, lo);
         hi = __reduce_or_sync(FULL, hi);
         const unsigned long long ow = (unsigned long long)lo | ((unsigned long long)hi << 32);
-        bool dup = false;                                // cluster.rs:108-120
-        for (int p = 0; p < it; ++p) dup |= (ws->seen[p] == ow);
-        if (dup) break;
-        __syncwarp();
-        if (lane == 0) ws->seen[it] = ow;
+        if (ITERATE) {
+            bool dup = false;                            // cluster.rs:108-120
+            for (int p = 0; p < it; ++p) dup |= (ws->seen[p] == ow);
+            if (dup) break;
+            __syncwarp();
+            if (lane == 0) ws->seen[it] = ow;
+        }
         // ordered weighted points: PW[m] = UW[order[m]]  (cluster.rs:126-132)
         if (lane < count) ws->PW[lane] = ws->UW[(ow >> (4 * lane)) & 15ull];
         if (lane <= count) ws->S[lane * 17 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -197,6 +257,7 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
         }
         __syncwarp();
         const float4 xsum = ws->S[count];                // == xsum_wsum (cluster.rs:125-133)
+        const f32x2 xs_xy = pk(xsum.x, xsum.y), xs_zw = pk(xsum.z, xsum.w);
 
         // ---- partition search ----------------------------------------------------------------------
         float lbest = __int_as_float(0x7F800000);
@@ -204,7 +265,7 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
         for (int c = lane; c < ncand; c += 32) {
             const uint32_t E = __ldg(tab + c);
             const float err = THREE ? eval3(ws->S, E, xsum, prm.wx, prm.wy, prm.wz, nullptr, false)
-                                    : eval4(ws->S, E, xsum, prm.wx, prm.wy, prm.wz, nullptr, false);
+                                    : eval4_packed(ws->S, E, xs_xy, xs_zw, prm.wx, prm.wy, prm.wz, prm.negzero2);
             if (err < lbest || (err == lbest && E < lE)) { lbest = err; lE = E; }
         }
         // lexicographic (error, loop order) argmin over the warp
@@ -227,6 +288,7 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const in
             for (int c = 0; c < 3; ++c) { bka[c] = sol.ka[c]; bkb[c] = sol.kb[c]; }
             bsx = sol.ax; bsy = sol.ay; bsz = sol.az; bex = sol.bx; bey = sol.by; bez = sol.bz;
         }
+        if (!ITERATE) break;
         if (best_iteration != it) break;                 // cluster.rs:243 / :383 (incl. quirk Q9)
         axx = sub(bex, bsx); axy = sub(bey, bsy); axz = sub(bez, bsz);      // :248 / :388
         __syncwarp();
@@ -466,15 +528,24 @@ __device__ uint2 colour_block(const uint32_t pix, const bool valid, const Encode
     if (prm.algorithm == RANGE_FIT) return range_fit<IS_BC1>(s, prm, principle, lane);
 
     // ---- ClusterFit (cluster.rs:49-76 + colourfit.rs:48-59) ----------------------------------------
-    const int niter = prm.algorithm == ITERATIVE_CLUSTER_FIT ? 8 : 1;
     float best_error = FLT_MAX;
     uint2 block = make_uint2(0u, 0u);
-    if (IS_BC1) {
-        cluster_pass<true>(s, prm, niter, principle, ws, tab3, lane, best_error, block);
-        __syncwarp();
-        if (!s.transparent) cluster_pass<false>(s, prm, niter, principle, ws, tab4, lane, best_error, block);
+    if (prm.algorithm == ITERATIVE_CLUSTER_FIT) {
+        if (IS_BC1) {
+            cluster_pass<true, true>(s, prm, principle, ws, tab3, lane, best_error, block);
+            __syncwarp();
+            if (!s.transparent) cluster_pass<false, true>(s, prm, principle, ws, tab4, lane, best_error, block);
+        } else {
+            cluster_pass<false, true>(s, prm, principle, ws, tab4, lane, best_error, block);
+        }
     } else {
-        cluster_pass<false>(s, prm, niter, principle, ws, tab4, lane, best_error, block);
+        if (IS_BC1) {
+            cluster_pass<true, false>(s, prm, principle, ws, tab3, lane, best_error, block);
+            __syncwarp();
+            if (!s.transparent) cluster_pass<false, false>(s, prm, principle, ws, tab4, lane, best_error, block);
+        } else {
+            cluster_pass<false, false>(s, prm, principle, ws, tab4, lane, best_error, block);
+        }
     }
     return block;
 }
