@@ -1,0 +1,62 @@
+"""Exact fp32 identities the CUDA kernels rely on, checked exhaustively in numpy float32
+(numpy float32 arithmetic is IEEE single, no contraction)."""
+import numpy as np
+
+f = np.float32
+
+
+def roundf(x):                      # libm roundf: half away from zero
+    return np.sign(x) * np.floor(np.abs(x) + f(0.5))
+
+
+def test_pack565_of_snapped_endpoint_is_the_grid_index():
+    # colourblock.rs:28-34 applied to k * fl(1/grid)  (cluster.rs:209-210, range.rs:97-98)
+    for grid in (31, 63):
+        k = np.arange(grid + 1, dtype=np.float32)
+        v = k * (f(1.0) / f(grid))
+        assert np.array_equal(np.clip(roundf(f(grid) * v), 0, grid), k)
+
+
+def test_pack565_of_single_colour_lut_endpoint_is_the_lut_value():
+    # single.rs:92-101: f32::from(s) / 31.0 then pack_565
+    for grid in (31, 63):
+        s = np.arange(grid + 1, dtype=np.float32)
+        assert np.array_equal(np.clip(roundf(f(grid) * (s / f(grid))), 0, grid), s)
+
+
+def test_single_colour_byte_roundtrip():
+    # single.rs:60-64 on colourset.rs:65-67: round((c/255)*255) == c
+    c = np.arange(256, dtype=np.float32)
+    assert np.array_equal(np.clip(roundf((c / f(255.0)) * f(255.0)), 0, 255), c)
+
+
+def test_weight_sums_are_exact_in_any_order():
+    # colourset.rs:70-97: sums of (alpha+1)/256 over up to 16 pixels are multiples of 2^-8 below 2^5 -> exact
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        a = rng.integers(0, 256, size=16)
+        w = (a + 1).astype(np.float32) / f(256.0)
+        seq = f(0.0)
+        for x in w:
+            seq = f(seq + x)
+        assert seq == f((a + 1).sum()) / f(256.0)
+
+
+def test_alpha_key_argmin_matches_first_min_of_squared_distance():
+    # alpha.rs:101-111 vs key_j = v*(-16*c_j) + (8*c_j^2 + j)  (txp_alpha.cuh fast path)
+    rng = np.random.default_rng(1)
+    for _ in range(3000):
+        codes = rng.integers(0, 256, size=8)
+        v = rng.integers(0, 256)
+        d2 = (v - codes) ** 2
+        ref = int(np.argmin(d2))                         # numpy argmin returns the first minimum
+        key = v * (-16 * codes) + 8 * codes * codes + np.arange(8)
+        assert int(np.argmin(key)) == ref and int(key.min()) & 7 == ref
+        assert (int(key.min()) - ref) // 8 + v * v == int(d2.min())
+
+
+def test_swap7_field_trick():
+    # write_alpha_block7 (alpha.rs:172-178): 0->1, 1->0, x->9-x  ==  (9 - f) & 7
+    for x in range(8):
+        want = 1 if x == 0 else 0 if x == 1 else 9 - x
+        assert (9 - x) & 7 == want
