@@ -60,3 +60,16 @@ def test_swap7_field_trick():
     for x in range(8):
         want = 1 if x == 0 else 0 if x == 1 else 9 - x
         assert (9 - x) & 7 == want
+
+
+def test_division_free_alpha_interpolants():
+    # txp_alpha.cuh alpha_codebooks_fast: ((N-i)*lo + i*hi)/N == lo + floor(i*(hi-lo)/N) with
+    # floor(x/5) == (x*205)>>10 for x <= 1020 and floor(x/7) == (x*9363)>>16 for x <= 1530
+    assert all((x * 205) >> 10 == x // 5 for x in range(1021))
+    assert all((x * 9363) >> 16 == x // 7 for x in range(1531))
+    for lo in range(0, 256, 5):
+        for hi in range(lo, 256, 3):
+            for i in range(1, 5):
+                assert ((5 - i) * lo + i * hi) // 5 == lo + ((i * 205 * (hi - lo)) >> 10)
+            for i in range(1, 7):
+                assert ((7 - i) * lo + i * hi) // 7 == lo + ((i * 9363 * (hi - lo)) >> 16)

@@ -147,13 +147,19 @@ __device__ __forceinline__ void make_keybook(const int codes[8], KeyBook& kb) {
     for (int j = 0; j < 8; ++j) { kb.a[j] = -16 * codes[j]; kb.b[j] = 8 * codes[j] * codes[j] + j; }
 }
 
-__device__ __forceinline__ int best_key(const int v, const KeyBook& kb) {
-    int k[8];
+// interpolated codes without integer division: ((N-i)*lo + i*hi)/N == lo + floor(i*(hi-lo)/N), and for
+// 0 <= x <= 1530 floor(x/5) == (x*205)>>10 (x <= 1020) and floor(x/7) == (x*9363)>>16  (checked exhaustively
+// in tests/test_identities.py)
+__device__ __forceinline__ void alpha_codebooks_fast(const int min5, const int max5, const int min7, const int max7,
+                                                     int codes5[8], int codes7[8]) {
+    const int r5 = max5 - min5, r7 = max7 - min7;
+    codes5[0] = min5; codes5[1] = max5;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) k[j] = v * kb.a[j] + kb.b[j];
-    const int m0 = __vimin3_s32(k[0], k[1], k[2]);
-    const int m1 = __vimin3_s32(k[3], k[4], k[5]);
-    return __vimin3_s32(m0, m1, min(k[6], k[7]));
+    for (int i = 1; i < 5; ++i) codes5[1 + i] = min5 + ((i * 205 * r5) >> 10);
+    codes5[6] = 0; codes5[7] = 255;
+    codes7[0] = min5; codes7[1] = max5;
+#pragma unroll
+    for (int i = 1; i < 7; ++i) codes7[1 + i] = min7 + ((i * 9363 * r7) >> 16);
 }
 
 // 24-bit words of eight 3-bit fields; EVEN3 selects fields 0,2,4,6 (6-bit lanes at bits 0,6,12,18)
@@ -195,7 +201,7 @@ __device__ __forceinline__ uint2 alpha_fit_full(const uint32_t v[16]) {
     fix_range(min5, max5, 5);
     fix_range(min7, max7, 7);
     int codes5[8], codes7[8];
-    alpha_codebooks(min5, max5, min7, max7, codes5, codes7);
+    alpha_codebooks_fast(min5, max5, min7, max7, codes5, codes7);
     KeyBook k5, k7;
     make_keybook(codes5, k5);
     make_keybook(codes7, k7);
@@ -203,7 +209,16 @@ __device__ __forceinline__ uint2 alpha_fit_full(const uint32_t v[16]) {
     uint32_t w5lo = 0, w5hi = 0, w7lo = 0, w7hi = 0;      // 3-bit indices, 8 per word
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int q5 = best_key((int)v[i], k5), q7 = best_key((int)v[i], k7);
+        // codes 0 and 1 (min5, max5) are the same in both books (alpha.rs:227-228, :238-239): shared keys
+        const int x = (int)v[i];
+        const int m01 = min(x * k5.a[0] + k5.b[0], x * k5.a[1] + k5.b[1]);
+        int k[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) k[j] = x * k5.a[2 + j] + k5.b[2 + j];
+        const int q5 = __vimin3_s32(__vimin3_s32(m01, k[0], k[1]), __vimin3_s32(k[2], k[3], k[4]), k[5]);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) k[j] = x * k7.a[2 + j] + k7.b[2 + j];
+        const int q7 = __vimin3_s32(__vimin3_s32(m01, k[0], k[1]), __vimin3_s32(k[2], k[3], k[4]), k[5]);
         s5 += q5; s7 += q7;
         const uint32_t sh = 1u << (3 * (i & 7));
         if (i < 8) { w5lo += ((uint32_t)q5 & 7u) * sh; w7lo += ((uint32_t)q7 & 7u) * sh; }
@@ -225,8 +240,8 @@ __device__ __forceinline__ uint2 alpha_fit_full(const uint32_t v[16]) {
 // Loads: 4 x 16-byte row segments per thread; consecutive threads read consecutive 16 B, so every warp
 // load instruction covers 512 contiguous bytes per image row (fully coalesced without staging).
 // Stores: 8 B (BC4) / 16 B (BC5) per thread, consecutive across the warp.
-template <int FMT>
-__global__ void __launch_bounds__(256) alpha_encode_kernel(const BlockSource src, uint8_t* __restrict__ out) {
+template <int FMT, int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_encode_kernel(const BlockSource src, uint8_t* __restrict__ out) {
     const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= src.nblocks) return;
     uint32_t px[16];
@@ -237,7 +252,8 @@ __global__ void __launch_bounds__(256) alpha_encode_kernel(const BlockSource src
         for (int r = 0; r < 4; ++r) { const uint4 q = __ldg(p + r); px[4 * r] = q.x; px[4 * r + 1] = q.y; px[4 * r + 2] = q.z; px[4 * r + 3] = q.w; }
         mask = src.masks[b] & 0xFFFFu;
     } else {
-        const uint32_t bx = (uint32_t)(b % src.bw), by = (uint32_t)(b / src.bw);
+        const uint32_t b32 = (uint32_t)b;                 // nblocks < 2^31 (checked by the host)
+        const uint32_t by = b32 / src.bw, bx = b32 - by * src.bw;
         const uint32_t x0 = 4 * bx, y0 = 4 * by;
         if (src.vec_ok && y0 + 4 <= src.h) {              // interior rows: x0+4 <= w because w % 4 == 0
             const uint8_t* base = src.rgba + ((size_t)y0 * src.w + x0) * 4;

@@ -6,6 +6,7 @@
 // every data path ends in a kernel launch or an error code.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(COLOUR_WARPS * 32) colour_encode_kernel(const 
             pix = __ldg(reinterpret_cast<const uint32_t*>(src.rgba) + b * 16 + lane);
             valid = (__ldg(src.masks + b) >> lane) & 1u;
         } else {
-            const uint32_t bx = (uint32_t)(b % src.bw), by = (uint32_t)(b / src.bw);
+            const uint32_t b32 = (uint32_t)b;                     // nblocks < 2^31 (checked by the host)
+            const uint32_t by = b32 / src.bw, bx = b32 - by * src.bw;
             const uint32_t sx = 4 * bx + (lane & 3), sy = 4 * by + (lane >> 2);
             valid = sx < src.w && sy < src.h;
             if (valid) pix = __ldg(reinterpret_cast<const uint32_t*>(src.rgba) + (size_t)sy * src.w + sx);
@@ -201,9 +203,29 @@ static int launch_encode(int format, const BlockSource& src, const txp_params* p
     if (src.nblocks > 0x7FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^31-1 blocks in one launch");
     const EncodeParams e = to_device_params(p);
     if (format == BC4 || format == BC5) {
-        const unsigned grid = (unsigned)((src.nblocks + 255) / 256);
-        if (format == BC4) alpha_encode_kernel<BC4><<<grid, 256, 0, st>>>(src, d_out);
-        else alpha_encode_kernel<BC5><<<grid, 256, 0, st>>>(src, d_out);
+        // launch shape (threads per CTA, min CTAs per SM -> register cap); TXP_ALPHA_VARIANT is a tuning knob
+        static const int variant = [] { const char* e = getenv("TXP_ALPHA_VARIANT"); return e ? atoi(e) : -1; }();
+#define TXP_ALPHA_LAUNCH(F, T, M) alpha_encode_kernel<F, T, M><<<(unsigned)((src.nblocks + (T) - 1) / (T)), T, 0, st>>>(src, d_out)
+        if (format == BC4) {
+            switch (variant) {
+            case 1: TXP_ALPHA_LAUNCH(BC4, 128, 8); break;
+            case 2: TXP_ALPHA_LAUNCH(BC4, 128, 6); break;
+            case 3: TXP_ALPHA_LAUNCH(BC4, 256, 3); break;
+            case 4: TXP_ALPHA_LAUNCH(BC4, 64, 16); break;
+            case 5: TXP_ALPHA_LAUNCH(BC4, 256, 4); break;
+            default: TXP_ALPHA_LAUNCH(BC4, 128, 8); break;   // 64 registers, 32 warps/SM: best of the sweep (profiles/README.md)
+            }
+        } else {
+            switch (variant) {
+            case 1: TXP_ALPHA_LAUNCH(BC5, 128, 8); break;
+            case 2: TXP_ALPHA_LAUNCH(BC5, 128, 6); break;
+            case 3: TXP_ALPHA_LAUNCH(BC5, 256, 3); break;
+            case 4: TXP_ALPHA_LAUNCH(BC5, 64, 16); break;
+            case 5: TXP_ALPHA_LAUNCH(BC5, 256, 4); break;
+            default: TXP_ALPHA_LAUNCH(BC5, 128, 6); break;   // 80 registers, 24 warps/SM
+            }
+        }
+#undef TXP_ALPHA_LAUNCH
     } else {
         const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
         const unsigned threads = COLOUR_WARPS * 32;

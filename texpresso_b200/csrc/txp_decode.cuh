@@ -38,29 +38,39 @@ __device__ __forceinline__ void decode_colour(const uint2 blk, const bool is_bc1
     for (int i = 0; i < 16; ++i) px[i] = codes[(blk.y >> (2 * i)) & 3u];
 }
 
-// alpha.rs:258-304 : writes the decoded value into byte `channel` of each pixel
+// 12 bits holding four 3-bit indices -> PRMT selector with the indices in its four nibbles
+__device__ __forceinline__ uint32_t spread3to4(const uint32_t x) {
+    const uint32_t y = (x & 0x03Fu) | ((x & 0xFC0u) << 2);            // two 6-bit groups in bytes 0 and 1
+    return (y & 0x0707u) | ((y & 0x3838u) << 1);                       // 0abc0def per byte
+}
+
+// alpha.rs:258-304 : writes the decoded value into byte `channel` of each pixel.
+// The 8-entry codebook lives in two registers; PRMT is a byte LUT indexed by the selector nibbles, so one
+// PRMT looks up four pixels and one more PRMT per pixel inserts the byte into the pixel word.
 __device__ __forceinline__ void decode_alpha3(const uint2 blk, const int channel, uint32_t px[16]) {
     const int a0 = (int)(blk.x & 255u), a1 = (int)((blk.x >> 8) & 255u);
-    uint32_t codes[8];
-    codes[0] = (uint32_t)a0; codes[1] = (uint32_t)a1;
+    uint32_t c[8];
+    c[0] = (uint32_t)a0; c[1] = (uint32_t)a1;
     if (a0 <= a1) {
 #pragma unroll
-        for (int i = 1; i < 5; ++i) codes[1 + i] = (uint32_t)(((5 - i) * a0 + i * a1) / 5);
-        codes[6] = 0u; codes[7] = 255u;
+        for (int i = 1; i < 5; ++i) c[1 + i] = (uint32_t)(((5 - i) * a0 + i * a1) / 5);
+        c[6] = 0u; c[7] = 255u;
     } else {
 #pragma unroll
-        for (int i = 1; i < 7; ++i) codes[1 + i] = (uint32_t)(((7 - i) * a0 + i * a1) / 7);
+        for (int i = 1; i < 7; ++i) c[1 + i] = (uint32_t)(((7 - i) * a0 + i * a1) / 7);
     }
+    const uint32_t lut_lo = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+    const uint32_t lut_hi = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
     const unsigned long long bits = ((unsigned long long)blk.y << 16) | (blk.x >> 16);   // 48 index bits
-    const uint32_t sh = 8u * (uint32_t)channel;
+    // selector that replaces byte `channel` of a pixel (first PRMT source) with byte k of the second source
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t idx = (uint32_t)(bits >> (3 * i)) & 7u;
-        // select without dynamic register indexing
-        uint32_t c = codes[0];
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t four = __byte_perm(lut_lo, lut_hi, spread3to4((uint32_t)(bits >> (12 * q)) & 0xFFFu));
 #pragma unroll
-        for (int j = 1; j < 8; ++j) c = idx == (uint32_t)j ? codes[j] : c;
-        px[i] = (px[i] & ~(255u << sh)) | (c << sh);
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t sel = (0x3210u & ~(0xFu << (4 * channel))) | ((4u + k) << (4 * channel));
+            px[4 * q + k] = __byte_perm(px[4 * q + k], four, sel);
+        }
     }
 }
 
@@ -85,7 +95,7 @@ __device__ __forceinline__ void decode_block(const uint8_t* __restrict__ data, c
         for (int i = 0; i < 16; ++i) px[i] = 0xFF000000u;
         decode_alpha3(q, 0, px);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const uint32_t r = px[i] & 255u; px[i] = 0xFF000000u | r | (r << 8) | (r << 16); }
+        for (int i = 0; i < 16; ++i) px[i] = __byte_perm(px[i], 0, 0x3000);     // (r, r, r, 255): lib.rs:264-268
     } else {
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(data) + b);
         if (FMT == BC5) {
@@ -116,7 +126,8 @@ __global__ void __launch_bounds__(256) decode_kernel(const uint8_t* __restrict__
         for (int r = 0; r < 4; ++r) o[r] = make_uint4(px[4 * r], px[4 * r + 1], px[4 * r + 2], px[4 * r + 3]);
         return;
     }
-    const uint32_t bx = (uint32_t)(b % bw), by = (uint32_t)(b / bw);
+    const uint32_t b32 = (uint32_t)b;                     // nblocks < 2^31 (checked by the host)
+    const uint32_t by = b32 / bw, bx = b32 - by * bw;
     const uint32_t x0 = 4 * bx, y0 = 4 * by;
     if (vec_ok && y0 + 4 <= h) {
         uint8_t* base = out + ((size_t)y0 * w + x0) * 4;
