@@ -18,6 +18,7 @@
 #include "txp_common.cuh"
 #include "txp_alpha.cuh"
 #include "txp_colour.cuh"
+#include "txp_range.cuh"
 #include "txp_decode.cuh"
 
 namespace txp {
@@ -129,6 +130,7 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         TXP_CUDA(cudaMemcpyToSymbol(g_tab4, t4.data(), TAB4_PAD * 4));
         TXP_CUDA(cudaMemcpyToSymbol(g_tab3, t3.data(), TAB3_PAD * 4));
         TXP_CUDA(cudaMemcpyToSymbol(c_single_lut, lut, sizeof lut));
+        TXP_CUDA(cudaMemcpyToSymbol(g_single_lut, lut, sizeof lut));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
@@ -226,6 +228,12 @@ static int launch_encode(int format, const BlockSource& src, const txp_params* p
             }
         }
 #undef TXP_ALPHA_LAUNCH
+    } else if (e.algorithm == RANGE_FIT) {
+        // RangeFit: one thread per block (txp_range.cuh)
+        const unsigned grid = (unsigned)((src.nblocks + 127) / 128);
+        if (format == BC1) range_encode_kernel<BC1><<<grid, 128, 0, st>>>(src, e, d_out);
+        else if (format == BC2) range_encode_kernel<BC2><<<grid, 128, 0, st>>>(src, e, d_out);
+        else range_encode_kernel<BC3><<<grid, 128, 0, st>>>(src, e, d_out);
     } else {
         const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
         const unsigned threads = COLOUR_WARPS * 32;

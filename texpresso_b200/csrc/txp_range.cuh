@@ -1,0 +1,305 @@
+// txp_range.cuh -- RangeFit encoder (BC1 / BC2 / BC3), one THREAD per 4x4 block.
+//
+// Replaces (reference): lib.rs:188-234 for Algorithm::RangeFit, colourset.rs:35-141, colourfit/range.rs:44-192,
+// colourfit/single.rs:58-164 (count == 1), math.rs:44-97, colourblock.rs:28-94, and the alpha half
+// (alpha.rs:27-51 / :187-256).
+//
+// RangeFit is ~2k dependent flops per block with no search to parallelise, so a warp per block (the ClusterFit
+// layout) wastes 31 lanes on the serial parts.  Here every lane owns a whole block:
+//   * the colour set is not compacted.  A pixel is "new" if no earlier active pixel has its RGB; all
+//     order-sensitive sums (math.rs:48-70, range.rs:129) run over the 16 pixels in order with weight / term 0 for
+//     pixels that are not new -- x + (+-0) is an exact no-op for accumulators that start at +0 -- which is the same
+//     left-to-right order as the reference's loops over the compacted set.
+//   * nearest-code indices are computed per pixel (duplicates of a point get the same answer), so no remap table.
+//   * c/255 comes from a 256-entry shared table built with IEEE division (colourset.rs:65-67).
+#pragma once
+#include <cfloat>
+#include "txp_common.cuh"
+#include "txp_alpha.cuh"
+
+namespace txp {
+
+__device__ uint8_t g_single_lut[6144];        // copy of the SingleColourFit table for per-thread (divergent) lookups
+
+// spread the low 16 bits of m to the even bit positions of a 32-bit word
+__device__ __forceinline__ uint32_t spread16(uint32_t m) {
+    m = (m | (m << 8)) & 0x00FF00FFu;
+    m = (m | (m << 4)) & 0x0F0F0F0Fu;
+    m = (m | (m << 2)) & 0x33333333u;
+    m = (m | (m << 1)) & 0x55555555u;
+    return m;
+}
+
+// single.rs:58-106 with per-thread table reads
+__device__ __forceinline__ void single_endpoints_thread(const uint32_t rgb, const int t0, const int t1, const int t2,
+                                                        uint32_t& a565, uint32_t& b565, uint32_t& index, uint32_t& error) {
+    const int tabs[3] = {t0, t1, t2};
+    const uint32_t col[3] = {rgb & 255u, (rgb >> 8) & 255u, (rgb >> 16) & 255u};
+    error = 0xFFFFFFFFu; a565 = 0; b565 = 0; index = 0;
+#pragma unroll
+    for (int idx = 0; idx < 2; ++idx) {
+        uint32_t e = 0, st[3], en[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint8_t* p = &g_single_lut[((tabs[c] * 256 + col[c]) * 2 + idx) * 3];
+            st[c] = __ldg(p); en[c] = __ldg(p + 1);
+            const uint32_t d = __ldg(p + 2);
+            e += d * d;
+        }
+        if (e < error) {
+            a565 = (st[0] << 11) | (st[1] << 5) | st[2];
+            b565 = (en[0] << 11) | (en[1] << 5) | en[2];
+            index = 2u * idx; error = e;
+        }
+    }
+}
+
+// single.rs:122-164 + colourfit.rs:48-59.  active16: pixels that carry the colour; others get index 3.
+template <bool IS_BC1>
+__device__ __forceinline__ uint2 single_fit_thread(const uint32_t rgb, const uint32_t active16, const bool transparent) {
+    const uint32_t act = spread16(active16), inact = spread16(~active16 & 0xFFFFu) * 3u;
+    uint32_t a, b, index, err, best = 0xFFFFFFFFu;
+    uint2 block = make_uint2(0u, 0u);
+    if (IS_BC1) {
+        single_endpoints_thread(rgb, 0, 1, 0, a, b, index, err);
+        block = write3_packed(a, b, act * index | inact);
+        best = err;
+        if (transparent) return block;
+    }
+    single_endpoints_thread(rgb, 2, 3, 2, a, b, index, err);
+    if (err < best) block = write4_packed(a, b, act * index | inact);
+    return block;
+}
+
+// alpha.rs:27-51, one thread
+__device__ __forceinline__ uint2 alpha_bc2_thread(const uint32_t px[16], const uint32_t mask) {
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float a = mul((float)(px[i] >> 24), 15.0f / 255.0f);
+        uint32_t q = (uint32_t)f32_to_i32_clamped(a, 15);
+        if (!((mask >> i) & 1u)) q = 0;
+        w[i >> 3] |= q << (4 * (i & 7));
+    }
+    return make_uint2(w[0], w[1]);
+}
+
+// Colour half of one block with Algorithm::RangeFit.  px: 16 RGBA words, mask: valid bits, lut: c/255 table.
+template <bool IS_BC1>
+__device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint32_t mask, const EncodeParams& prm,
+                                                     const float* __restrict__ lut) {
+    // ---- ColourSet (colourset.rs:35-112) ----------------------------------------------------------------
+    uint32_t active16 = 0, punched = 0;
+    uint32_t wgt[16];                                   // integer weight of pixel i: 1, or alpha+1 (exact sums)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool valid = (mask >> i) & 1u;
+        const bool pt = IS_BC1 && valid && (px[i] >> 24) < 128u;                  // :54
+        if (pt) punched |= 1u << i;
+        if (valid && !pt) active16 |= 1u << i;
+        wgt[i] = prm.alpha_weighted ? (px[i] >> 24) + 1u : 1u;
+        // key: RGB for active pixels, a unique value otherwise (never equal to anything)
+        px[i] = (valid && !pt) ? (px[i] & 0x00FFFFFFu) : (0x01000000u | (uint32_t)i);
+    }
+    const bool transparent = punched != 0;
+    if (active16 == 0)                                   // lib.rs:223, SURVEY Q14
+        return IS_BC1 ? make_uint2(0u, 0xFFFFFFFFu) : make_uint2(0u, 0u);
+    // exact-RGB duplicates (:84-88): pixel i is new iff no earlier pixel has its key; group weights are
+    // accumulated on every earlier equal pixel (only the first one's total is used)
+    uint32_t dup16 = 0;
+    uint32_t gw[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gw[i] = wgt[i];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+        bool dup = false;
+#pragma unroll
+        for (int j = 0; j < i; ++j) {
+            const bool eq = px[i] == px[j];
+            dup |= eq;
+            if (eq) gw[j] += wgt[i];
+        }
+        if (dup) dup16 |= 1u << i;
+    }
+    const uint32_t new16 = active16 & ~dup16;
+    if ((new16 & (new16 - 1u)) == 0u) {                  // exactly one distinct colour: lib.rs:217-222
+        uint32_t rgb = 0;                                // every active pixel carries it
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if ((active16 >> i) & 1u) rgb |= px[i];
+        return single_fit_thread<IS_BC1>(rgb, active16, transparent);
+    }
+
+    // weights: sqrt of the group totals (:107-109); 0 for pixels that are not new
+    float w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool is_new = (new16 >> i) & 1u;
+        float t = 0.0f;
+        if (is_new) {
+            t = 1.0f;
+            if (gw[i] != 1u || prm.alpha_weighted)
+                t = __fsqrt_rn(prm.alpha_weighted ? mul((float)gw[i], 1.0f / 256.0f) : (float)gw[i]);
+        }
+        w[i] = t;
+    }
+
+    // ---- Sym3x3::weighted_covariance (math.rs:44-73) --------------------------------------------------------
+    float total = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float x = lut[px[i] & 255u], y = lut[(px[i] >> 8) & 255u], z = lut[(px[i] >> 16) & 255u];
+        total = add(total, w[i]);
+        cx = add(cx, mul(x, w[i])); cy = add(cy, mul(y, w[i])); cz = add(cz, mul(z, w[i]));
+    }
+    if (total > FLT_EPSILON) { cx = fdiv(cx, total); cy = fdiv(cy, total); cz = fdiv(cz, total); }
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float x = lut[px[i] & 255u], y = lut[(px[i] >> 8) & 255u], z = lut[(px[i] >> 16) & 255u];
+        const float ax = sub(x, cx), ay = sub(y, cy), az = sub(z, cz);
+        const float bx = mul(ax, w[i]), by = mul(ay, w[i]), bz = mul(az, w[i]);
+        m0 = add(m0, mul(ax, bx)); m1 = add(m1, mul(ax, by)); m2 = add(m2, mul(ax, bz));
+        m3 = add(m3, mul(ay, by)); m4 = add(m4, mul(ay, bz)); m5 = add(m5, mul(az, bz));
+    }
+    // ---- principle_component (math.rs:75-97) ----------------------------------------------------------------
+    float vx = 1.0f, vy = 1.0f, vz = 1.0f;
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        const float tx = add(mul(m2, vz), add(mul(m1, vy), mul(m0, vx)));
+        const float ty = add(mul(m4, vz), add(mul(m3, vy), mul(m1, vx)));
+        const float tz = add(mul(m5, vz), add(mul(m4, vy), mul(m2, vx)));
+        const float ra = rcp(fmaxf(tx, fmaxf(ty, tz)));
+        vx = mul(tx, ra); vy = mul(ty, ra); vz = mul(tz, ra);
+    }
+    // ---- range.rs:67-86: first point starts both ends; strict < / else-if > over the following points ----------
+    uint32_t ps = 0, pe = 0;
+    float mn = 0.f, mx = 0.f;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool is_new = (new16 >> i) & 1u;
+        const float x = lut[px[i] & 255u], y = lut[(px[i] >> 8) & 255u], z = lut[(px[i] >> 16) & 255u];
+        const float d = add(add(mul(x, vx), mul(y, vy)), mul(z, vz));
+        const bool first = is_new && !found;
+        const bool lower = is_new && found && d < mn;
+        const bool upper = is_new && found && !(d < mn) && d > mx;
+        if (first || lower) { ps = px[i]; mn = d; }
+        if (first || upper) { pe = px[i]; mx = d; }
+        found = found || is_new;
+    }
+    // clamp to [0,1] is the identity on c/255; snap to the 5:6:5 grid (range.rs:88-98)
+    const float grid[3] = {31.0f, 63.0f, 31.0f};
+    const float gridrcp[3] = {1.0f / 31.0f, 1.0f / 63.0f, 1.0f / 31.0f};
+    float sv[3], ev[3];
+    uint32_t ks[3], ke[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = grid_index(grid[c], lut[(ps >> (8 * c)) & 255u]);
+        const float b = grid_index(grid[c], lut[(pe >> (8 * c)) & 255u]);
+        ks[c] = (uint32_t)a; ke[c] = (uint32_t)b;
+        sv[c] = mul(a, gridrcp[c]); ev[c] = mul(b, gridrcp[c]);
+    }
+    const uint32_t a565 = (ks[0] << 11) | (ks[1] << 5) | ks[2];
+    const uint32_t b565 = (ke[0] << 11) | (ke[1] << 5) | ke[2];
+    const float mw[3] = {prm.wx, prm.wy, prm.wz};
+    const uint32_t inact = spread16(~active16 & 0xFFFFu) * 3u;                   // colourset.rs:134-137
+
+    // ---- compress3 / compress4 (range.rs:103-192, colourfit.rs:48-59) -------------------------------------------
+    float best_error = FLT_MAX;
+    uint2 block = make_uint2(0u, 0u);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool three = pass == 0;
+        if (three && !IS_BC1) continue;
+        if (!three && IS_BC1 && transparent) continue;
+        float codes[4][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            codes[0][c] = sv[c]; codes[1][c] = ev[c];
+            if (three) {
+                codes[2][c] = add(mul(sv[c], 0.5f), mul(ev[c], 0.5f));
+                codes[3][c] = 0.f;
+            } else {
+                codes[2][c] = add(mul(sv[c], 2.0f / 3.0f), mul(ev[c], 1.0f / 3.0f));
+                codes[3][c] = add(mul(sv[c], 1.0f / 3.0f), mul(ev[c], 2.0f / 3.0f));
+            }
+        }
+        float error = 0.0f;
+        uint32_t idx2 = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float p[3] = {lut[px[i] & 255u], lut[(px[i] >> 8) & 255u], lut[(px[i] >> 16) & 255u]};
+            float dist = FLT_MAX; uint32_t idx = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (three && j == 3) continue;
+                const float dx = mul(mw[0], sub(p[0], codes[j][0]));
+                const float dy = mul(mw[1], sub(p[1], codes[j][1]));
+                const float dz = mul(mw[2], sub(p[2], codes[j][2]));
+                const float d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+                if (d < dist) { dist = d; idx = (uint32_t)j; }                     // range.rs:118 (strict: first wins)
+            }
+            error = add(error, ((new16 >> i) & 1u) ? dist : 0.0f);                // range.rs:129, set order
+            idx2 += idx << (2 * i);
+        }
+        if (error < best_error) {                                                  // range.rs:133
+            best_error = error;
+            const uint32_t word = (idx2 & (spread16(active16) * 3u)) | inact;
+            block = three ? write3_packed(a565, b565, word) : write4_packed(a565, b565, word);
+        }
+    }
+    return block;
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(128) range_encode_kernel(const BlockSource src, const EncodeParams prm, uint8_t* __restrict__ out) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = fdiv((float)i, 255.0f);   // colourset.rs:65-67
+    __syncthreads();
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= src.nblocks) return;
+    uint32_t px[16];
+    uint32_t mask;
+    if (src.masks) {
+        const uint4* p = reinterpret_cast<const uint4*>(src.rgba) + b * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const uint4 q = __ldg(p + r); px[4 * r] = q.x; px[4 * r + 1] = q.y; px[4 * r + 2] = q.z; px[4 * r + 3] = q.w; }
+        mask = __ldg(src.masks + b) & 0xFFFFu;
+    } else {
+        const uint32_t b32 = (uint32_t)b;
+        const uint32_t by = b32 / src.bw, bx = b32 - by * src.bw;
+        const uint32_t x0 = 4 * bx, y0 = 4 * by;
+        if (src.vec_ok && y0 + 4 <= src.h) {
+            const uint8_t* base = src.rgba + ((size_t)y0 * src.w + x0) * 4;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * src.w * 4));
+                px[4 * r] = q.x; px[4 * r + 1] = q.y; px[4 * r + 2] = q.z; px[4 * r + 3] = q.w;
+            }
+            mask = 0xFFFFu;
+        } else {
+            mask = 0;
+            const uint32_t* img = reinterpret_cast<const uint32_t*>(src.rgba);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t sx = x0 + (i & 3), sy = y0 + (i >> 2);
+                px[i] = 0;
+                if (sx < src.w && sy < src.h) { px[i] = __ldg(img + (size_t)sy * src.w + sx); mask |= 1u << i; }
+            }
+        }
+    }
+    uint2 alpha_half = make_uint2(0u, 0u);
+    if (FMT == BC2) alpha_half = alpha_bc2_thread(px, mask);
+    if (FMT == BC3) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = px[i] >> 24;
+        alpha_half = mask == 0xFFFFu ? alpha_fit_full(v) : alpha_fit_thread(v, mask);
+    }
+    const uint2 colour = range_colour_thread<FMT == BC1>(px, mask, prm, lut);
+    if (FMT == BC1) reinterpret_cast<uint2*>(out)[b] = colour;
+    else reinterpret_cast<uint4*>(out)[b] = make_uint4(alpha_half.x, alpha_half.y, colour.x, colour.y);
+}
+
+}  // namespace txp
