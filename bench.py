@@ -153,6 +153,9 @@ def run_ours(args):
     T.set_device(local)
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -280,7 +283,10 @@ def run_ours(args):
             "roofline": {"kernel": "colour_encode_kernel<BC3> (ClusterFit, 16 colours/block)", "bound": "fp32_issue",
                          "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": f"derived: {props.multi_processor_count} SMs x 128 lanes x {sm_max:.0f} MHz (MEASURED_PEAKS sm_max_mhz), 1 flop per lane-instruction (no FMA contraction allowed)",
-                         "flops_per_block": FLOPS_BC3, "traffic": None,
+                         "flops_per_block": FLOPS_BC3,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one 8192^2 launch (ncu --set full,
+                         # profiles/ncu_colour_r01_summary.json: 272.3 MB + 53.2 MB; algorithmic 268.4 + 67.1 MB), scaled to this rank's blocks
+                         "traffic": int(325.49e6 * blocks_rank / 4194304),
                          "hbm_context": {"achieved_gbs": bc3_gbs, "peak_gbs": hbm_peak, "frac": bc3_gbs / hbm_peak}},
             "paths_agree": same,
         }

@@ -6,7 +6,7 @@ import os, pathlib, shutil, subprocess, sys
 
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-OUT = HERE / "libtexpresso_b200.so"
+OUT = pathlib.Path(os.environ.get("TXP_BUILD_OUT", HERE / "libtexpresso_b200.so"))
 SOURCES = [CSRC / "txp_api.cu"]
 HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [HERE.parent / "include" / "texpresso_b200.h"]
 
@@ -34,6 +34,7 @@ def up_to_date():
 def build(force=False, verbose=False, extra=()):
     if not force and up_to_date():
         return OUT
+    extra = list(extra) + os.environ.get("TXP_BUILD_DEFS", "").split()
     cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(OUT), *map(str, SOURCES)]
     if verbose:
         print(" ".join(cmd))

@@ -26,8 +26,11 @@ namespace txp {
 // ---------------------------------------------------------------------------------------------------
 // BC1/BC2/BC3 encoder kernel: one warp per block (see txp_colour.cuh)
 // ---------------------------------------------------------------------------------------------------
+#ifndef TXP_COLOUR_MIN_CTAS
+#define TXP_COLOUR_MIN_CTAS 4
+#endif
 template <int FMT>
-__global__ void __launch_bounds__(COLOUR_WARPS * 32) colour_encode_kernel(const BlockSource src, const EncodeParams prm,
+__global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour_encode_kernel(const BlockSource src, const EncodeParams prm,
                                                                           uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem);

@@ -18,6 +18,12 @@
 #include <cfloat>
 #include "txp_common.cuh"
 
+#ifndef TXP_SEARCH_UNROLL
+#define TXP_SEARCH_UNROLL 2          // candidates per lane and loop trip in the partition search (A/B: profiles/README.md)
+#endif
+#define TXP_PRAGMA_(x) _Pragma(#x)
+#define TXP_UNROLL(n) TXP_PRAGMA_(unroll n)
+
 namespace txp {
 
 constexpr int COLOUR_WARPS = 8;                      // warps (= blocks) per CTA
@@ -262,6 +268,7 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const fl
         // ---- partition search ----------------------------------------------------------------------
         float lbest = __int_as_float(0x7F800000);
         uint32_t lE = 0xFFFFFFFFu;
+        TXP_UNROLL(TXP_SEARCH_UNROLL)
         for (int c = lane; c < ncand; c += 32) {
             const uint32_t E = __ldg(tab + c);
             const float err = THREE ? eval3(ws->S, E, xsum, prm.wx, prm.wy, prm.wz, nullptr, false)
