@@ -105,6 +105,17 @@ TXP_API int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len,
 TXP_API int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* widths, const size_t* heights,
                                size_t n_textures, const txp_params* params, uint8_t* const* outputs, int n_gpus);
 
+/* ---- mip chains (extension: the reference generates no mips, cli/src/main.rs:153) ------------------------------------ */
+/* Levels: (w,h), (max(1,w/2), max(1,h/2)), ... down to 1x1; each level is the 2x2 box filter (a+b+c+d+2)>>2 of the
+ * previous one (edge-clamped), generated on the device.  Output: the levels' blocks concatenated, level 0 first. */
+TXP_API int txp_mip_levels(size_t width, size_t height);
+TXP_API size_t txp_mipchain_compressed_size(int format, size_t width, size_t height);
+TXP_API int txp_compress_mipchain(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height,
+                                  const txp_params* params, uint8_t* output, size_t output_len);
+/* Batch of textures, each encoded with its full mip chain; texture t -> device t % n_gpus, copies overlapped with kernels. */
+TXP_API int txp_compress_batch_mips(int format, const uint8_t* const* rgba, const size_t* widths, const size_t* heights,
+                                    size_t n_textures, const txp_params* params, uint8_t* const* outputs, int n_gpus);
+
 /* ---- runtime ------------------------------------------------------------------------------------------ */
 TXP_API int txp_device_count(void);          /* number of CUDA devices, or TXP_ERR_CUDA */
 TXP_API int txp_set_device(int device);      /* cudaSetDevice for the calling thread */

@@ -238,3 +238,28 @@ def test_multi_gpu_matches_single(T):
         one = T.Format(fmt).compress(img, w, h, tp)
         for n in (2, T.device_count()):
             assert np.array_equal(T.compress_multi(fmt, img, w, h, tp, n_gpus=n), one)
+
+
+# ---- mip chains (extension, BASELINE config 5): device mip filter + one-launch multi-level encode -----------------
+@pytest.mark.parametrize("w,h", [(64, 64), (100, 36), (16, 4), (1, 1), (5, 3), (256, 128)])
+@pytest.mark.parametrize("fmt,alg", [(0, 0), (2, 1), (4, 1), (1, 2)])
+def test_mipchain_matches_oracle_per_level(T, fmt, alg, w, h):
+    from texpresso_b200 import synth
+    img = synth.generate("smooth" if w >= 8 else "noise_alpha", w, h, seed=77)
+    tp, op = _params(T, alg, O.PERCEPTUAL)
+    got = T.compress_mipchain(fmt, img, w, h, tp)
+    want = np.concatenate([O.compress(fmt, lv, lv.shape[1], lv.shape[0], op) for lv in T.generate_mips(img, w, h)])
+    assert got.size == want.size
+    assert np.array_equal(got, want)
+
+
+def test_batch_with_mips_matches_single_calls(T):
+    from texpresso_b200 import synth
+    tp, _ = _params(T, 1, O.PERCEPTUAL)
+    texs = [(synth.generate("smooth", 64 >> (t % 3), 32, seed=100 + t), 64 >> (t % 3), 32) for t in range(7)]
+    outs = T.compress_batch_mips(2, texs, tp, n_gpus=1)
+    for (img, w, h), o in zip(texs, outs):
+        assert np.array_equal(o, T.compress_mipchain(2, img, w, h, tp))
+    if T.device_count() >= 2:
+        outs2 = T.compress_batch_mips(2, texs, tp, n_gpus=2)
+        assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))

@@ -69,3 +69,29 @@ def test_synth_is_counter_based():
     assert (n[..., 3] == 255).all() and len(np.unique(n[..., 0])) > 50
     r = synth.generate("r_rg", 16, 4, 4)
     assert (r[..., 2] == 0).all() and (r[..., 3] == 255).all()
+
+
+def test_mip_levels_and_sizes():
+    import texpresso_b200 as T
+    from texpresso_b200 import _lib
+    L = _lib.load()
+    assert T.mip_levels(1024, 1024)[-1] == (1, 1) and len(T.mip_levels(1024, 1024)) == 11
+    assert T.mip_levels(100, 36) == [(100, 36), (50, 18), (25, 9), (12, 4), (6, 2), (3, 1), (1, 1)]
+    for (w, h) in ((1024, 1024), (100, 36), (1, 1), (5, 3)):
+        lv = T.mip_levels(w, h)
+        assert L.txp_mip_levels(w, h) == len(lv)
+        for fmt in range(5):
+            assert L.txp_mipchain_compressed_size(fmt, w, h) == sum(T.Format(fmt).compressed_size(a, b) for a, b in lv)
+    # 87 381 blocks per 1024^2 texture with its full chain (65536+16384+...+1+1+1)
+    assert L.txp_mipchain_compressed_size(2, 1024, 1024) // 16 == 87383
+
+
+def test_generate_mips_box_filter():
+    import texpresso_b200 as T
+    img = np.arange(4 * 6 * 4, dtype=np.uint8).reshape(4, 6, 4)
+    lv = T.generate_mips(img, 6, 4)
+    assert [l.shape[:2] for l in lv] == [(4, 6), (2, 3), (1, 1)]
+    a = img.astype(np.int32)
+    assert np.array_equal(lv[1][0, 0], (a[0, 0] + a[0, 1] + a[1, 0] + a[1, 1] + 2) >> 2)
+    b = lv[1].astype(np.int32)                       # 3 wide -> 1 wide: columns 0,1 (clamped sampling never reaches col 2)
+    assert np.array_equal(lv[2][0, 0], (b[0, 0] + b[0, 1] + b[1, 0] + b[1, 1] + 2) >> 2)

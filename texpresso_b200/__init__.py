@@ -21,7 +21,7 @@ from ._lib import CParams, TexpressoError, check, load
 
 __all__ = ["Format", "Algorithm", "Params", "ColourWeights", "COLOUR_WEIGHTS_UNIFORM", "COLOUR_WEIGHTS_PERCEPTUAL",
            "num_blocks", "TexpressoError", "shard_rows", "compress_multi", "compress_batch", "compress_blocks",
-           "decompress_blocks", "device_count", "set_device", "kernel_launches", "version"]
+           "decompress_blocks", "mip_levels", "generate_mips", "compress_mipchain", "compress_batch_mips", "device_count", "set_device", "kernel_launches", "version"]
 
 ColourWeights = tuple
 COLOUR_WEIGHTS_UNIFORM = (1.0, 1.0, 1.0)                 # lib.rs:71
@@ -179,6 +179,56 @@ def compress_batch(fmt, textures, params=None, n_gpus=1):
     cp = params._c()
     check(load().txp_compress_batch(int(fmt), ins, ws, hs, n, ctypes.byref(cp), ous, n_gpus))
     return outs
+
+
+def mip_levels(width, height):
+    """[(w, h), ...] of the mip chain down to 1x1 (each dimension halves, floor, min 1)."""
+    out, w, h = [], int(width), int(height)
+    while True:
+        out.append((w, h))
+        if w == 1 and h == 1:
+            return out
+        w, h = max(1, w // 2), max(1, h // 2)
+
+
+def generate_mips(rgba, width, height):
+    """Host (numpy) statement of the device mip filter, for tests and tools: 2x2 box, (a+b+c+d+2)>>2, edge-clamped."""
+    lv = [np.asarray(rgba, dtype=np.uint8).reshape(height, width, 4)]
+    for (w, h) in mip_levels(width, height)[1:]:
+        s = lv[-1].astype(np.uint16)
+        sh, sw = s.shape[:2]
+        ys0 = np.minimum(2 * np.arange(h), sh - 1); ys1 = np.minimum(2 * np.arange(h) + 1, sh - 1)
+        xs0 = np.minimum(2 * np.arange(w), sw - 1); xs1 = np.minimum(2 * np.arange(w) + 1, sw - 1)
+        acc = s[ys0][:, xs0] + s[ys0][:, xs1] + s[ys1][:, xs0] + s[ys1][:, xs1] + 2
+        lv.append((acc >> 2).astype(np.uint8))
+    return lv
+
+
+def compress_mipchain(fmt, rgba, width, height, params=None):
+    """Encodes a texture and its device-generated mip chain; returns the concatenated blocks (level 0 first)."""
+    rgba = _u8(rgba, "rgba")
+    params = params or Params()
+    out = np.empty(load().txp_mipchain_compressed_size(int(fmt), width, height), dtype=np.uint8)
+    cp = params._c()
+    check(load().txp_compress_mipchain(int(fmt), _ptr(rgba), rgba.size, width, height, ctypes.byref(cp), _ptr(out), out.size))
+    return out
+
+
+def compress_batch_mips(fmt, textures, params=None, n_gpus=1, outputs=None):
+    """textures: list of (rgba uint8 array, width, height); each is encoded with its full mip chain on device t % n_gpus."""
+    params = params or Params()
+    n = len(textures)
+    arrs = [_u8(t[0], "rgba") for t in textures]
+    if outputs is None:
+        outputs = [np.empty(load().txp_mipchain_compressed_size(int(fmt), t[1], t[2]), dtype=np.uint8) for t in textures]
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    ins = (vp * n)(*[a.ctypes.data for a in arrs])
+    ous = (vp * n)(*[o.ctypes.data for o in outputs])
+    ws = (sz * n)(*[t[1] for t in textures])
+    hs = (sz * n)(*[t[2] for t in textures])
+    cp = params._c()
+    check(load().txp_compress_batch_mips(int(fmt), ins, ws, hs, n, ctypes.byref(cp), ous, n_gpus))
+    return outputs
 
 
 def device_count():

@@ -12,6 +12,7 @@ EXPORTS = [
     "txp_num_blocks", "txp_block_size", "txp_compressed_size", "txp_compress", "txp_decompress",
     "txp_compress_block_masked", "txp_decompress_block", "txp_compress_blocks", "txp_decompress_blocks",
     "txp_compress_device", "txp_decompress_device", "txp_shard_rows", "txp_compress_multi", "txp_compress_batch",
+    "txp_mip_levels", "txp_mipchain_compressed_size", "txp_compress_mipchain", "txp_compress_batch_mips",
     "txp_device_count", "txp_set_device", "txp_last_error", "txp_kernel_launches", "txp_version",
 ]
 
@@ -54,6 +55,10 @@ def load():
         "txp_shard_rows": (None, [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]),
         "txp_compress_multi": (ci, [ci, vp, sz, sz, sz, pp, vp, sz, ci]),
         "txp_compress_batch": (ci, [ci, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, pp, ctypes.POINTER(vp), ci]),
+        "txp_mip_levels": (ci, [sz, sz]),
+        "txp_mipchain_compressed_size": (sz, [ci, sz, sz]),
+        "txp_compress_mipchain": (ci, [ci, vp, sz, sz, sz, pp, vp, sz]),
+        "txp_compress_batch_mips": (ci, [ci, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, pp, ctypes.POINTER(vp), ci]),
         "txp_device_count": (ci, []),
         "txp_set_device": (ci, [ci]),
         "txp_last_error": (ctypes.c_char_p, []),

@@ -246,34 +246,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_encode_kernel(const B
     if (b >= src.nblocks) return;
     uint32_t px[16];
     uint32_t mask;
-    if (src.masks) {                                      // list mode
-        const uint4* p = reinterpret_cast<const uint4*>(src.rgba) + b * 4;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { const uint4 q = __ldg(p + r); px[4 * r] = q.x; px[4 * r + 1] = q.y; px[4 * r + 2] = q.z; px[4 * r + 3] = q.w; }
-        mask = src.masks[b] & 0xFFFFu;
-    } else {
-        const uint32_t b32 = (uint32_t)b;                 // nblocks < 2^31 (checked by the host)
-        const uint32_t by = b32 / src.bw, bx = b32 - by * src.bw;
-        const uint32_t x0 = 4 * bx, y0 = 4 * by;
-        if (src.vec_ok && y0 + 4 <= src.h) {              // interior rows: x0+4 <= w because w % 4 == 0
-            const uint8_t* base = src.rgba + ((size_t)y0 * src.w + x0) * 4;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(base + (size_t)r * src.w * 4));
-                px[4 * r] = q.x; px[4 * r + 1] = q.y; px[4 * r + 2] = q.z; px[4 * r + 3] = q.w;
-            }
-            mask = 0xFFFFu;
-        } else {                                          // edge blocks: per-pixel guarded loads (lib.rs:321)
-            mask = 0;
-            const uint32_t* img = reinterpret_cast<const uint32_t*>(src.rgba);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t sx = x0 + (i & 3), sy = y0 + (i >> 2);
-                px[i] = 0;
-                if (sx < src.w && sy < src.h) { px[i] = __ldg(img + (size_t)sy * src.w + sx); mask |= 1u << i; }
-            }
-        }
-    }
+    load_block_thread(src, b, px, mask);
     uint32_t v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = px[i] & 255u;    // channel 0 (lib.rs:200, :202)

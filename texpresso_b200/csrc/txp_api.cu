@@ -48,11 +48,10 @@ __global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour
             pix = __ldg(reinterpret_cast<const uint32_t*>(src.rgba) + b * 16 + lane);
             valid = (__ldg(src.masks + b) >> lane) & 1u;
         } else {
-            const uint32_t b32 = (uint32_t)b;                     // nblocks < 2^31 (checked by the host)
-            const uint32_t by = b32 / src.bw, bx = b32 - by * src.bw;
-            const uint32_t sx = 4 * bx + (lane & 3), sy = 4 * by + (lane >> 2);
-            valid = sx < src.w && sy < src.h;
-            if (valid) pix = __ldg(reinterpret_cast<const uint32_t*>(src.rgba) + (size_t)sy * src.w + sx);
+            const BlockPos bp = locate_block(src, (uint32_t)b);     // nblocks < 2^31 (checked by the host)
+            const uint32_t sx = bp.x0 + (lane & 3), sy = bp.y0 + (lane >> 2);
+            valid = sx < bp.w && sy < bp.h;
+            if (valid) pix = __ldg(reinterpret_cast<const uint32_t*>(bp.base) + (size_t)sy * bp.w + sx);
         }
     }
     uint2 alpha_half = make_uint2(0u, 0u);
@@ -63,6 +62,24 @@ __global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour
         if (FMT == BC1) reinterpret_cast<uint2*>(out)[b] = colour;
         else reinterpret_cast<uint4*>(out)[b] = make_uint4(alpha_half.x, alpha_half.y, colour.x, colour.y);   // lib.rs:213
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2x2 box-filter mip level (harness-defined: the reference has no mip generation):
+// dst(x,y) = (a + b + c + d + 2) >> 2 per channel over src(2x..2x+1, 2y..2y+1), coordinates clamped to the edge.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mip_downsample_kernel(const uint32_t* __restrict__ src, const uint32_t sw, const uint32_t sh,
+                                                             uint32_t* __restrict__ dst, const uint32_t dw, const uint32_t dh) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dw * dh) return;
+    const uint32_t y = i / dw, x = i - y * dw;
+    const uint32_t x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+    const uint32_t a = __ldg(src + (size_t)y0 * sw + x0), b = __ldg(src + (size_t)y0 * sw + x1);
+    const uint32_t c = __ldg(src + (size_t)y1 * sw + x0), d = __ldg(src + (size_t)y1 * sw + x1);
+    const uint32_t m = 0x00FF00FFu;
+    const uint32_t even = (((a & m) + (b & m) + (c & m) + (d & m) + 0x00020002u) >> 2) & m;
+    const uint32_t odd = ((((a >> 8) & m) + ((b >> 8) & m) + ((c >> 8) & m) + ((d >> 8) & m) + 0x00020002u) >> 2) & m;
+    dst[i] = even | (odd << 8);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -272,6 +289,7 @@ static BlockSource image_source(const uint8_t* d_rgba, size_t w, size_t h, uint6
     s.rgba = d_rgba; s.masks = nullptr;
     s.w = (uint32_t)w; s.h = (uint32_t)h; s.bw = (uint32_t)((w + 3) / 4);
     s.nblocks = nblocks;
+    s.nlevels = 1;
     s.vec_ok = ((w % 4) == 0 && (reinterpret_cast<uintptr_t>(d_rgba) % 16) == 0) ? 1 : 0;
     return s;
 }
@@ -352,6 +370,65 @@ static int compress_checked(int format, const uint8_t* rgba, size_t rgba_len, si
     const size_t need = txp_compressed_size(format, w, h);
     if (output_len < need) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than compressed_size (reference asserts, lib.rs:295)");
     if (output_len % (size_t)block_bytes(format)) return fail(TXP_ERR_ARGUMENT, "output_len is not a whole number of blocks");
+    return TXP_OK;
+}
+
+
+// ---- mip chains (extension; SURVEY 8(f) row 4 / BASELINE config 5) -------------------------------------------------
+static int mip_layout(int format, size_t w, size_t h, BlockSource* src, size_t* total_px, size_t* total_out) {
+    int n = 0; size_t px = 0; uint64_t blocks = 0;
+    size_t lw = w, lh = h;
+    while (true) {
+        if (n >= MAX_LEVELS) return fail(TXP_ERR_DIMENSIONS, "more than 16 mip levels");
+        if (src) { src->lw[n] = (uint32_t)lw; src->lh[n] = (uint32_t)lh; src->loff[n] = (uint32_t)px; src->lfirst[n] = (uint32_t)blocks; }
+        px += lw * lh; blocks += (uint64_t)txp_num_blocks(lw) * txp_num_blocks(lh);
+        ++n;
+        if (lw == 1 && lh == 1) break;
+        lw = lw > 1 ? lw / 2 : 1; lh = lh > 1 ? lh / 2 : 1;
+    }
+    if (px > 0xFFFFFFFFull || blocks > 0x7FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "mip chain too large");
+    if (src) { src->lfirst[n] = (uint32_t)blocks; src->nlevels = n; src->nblocks = blocks; }
+    if (total_px) *total_px = px;
+    if (total_out) *total_out = (size_t)blocks * (size_t)block_bytes(format);
+    return n;
+}
+
+// enqueue H2D(level 0) -> mip kernels -> one encode launch -> D2H on slot s; the caller waits on the slot
+static int mipchain_enqueue(Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output) {
+    BlockSource src;
+    size_t total_px = 0, total_out = 0;
+    int n = mip_layout(format, w, h, &src, &total_px, &total_out);
+    if (n < 0) return n;
+    int rc;
+    if ((rc = grow_dev(&s.d_in, &s.d_in_cap, total_px * 4)) != TXP_OK) return rc;
+    if ((rc = grow_dev(&s.d_out, &s.d_out_cap, total_out)) != TXP_OK) return rc;
+    const size_t in_bytes = w * h * 4;
+    const uint8_t* src_ptr = rgba;
+    if (!dma_direct(rgba)) {
+        if ((rc = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) return rc;
+        std::memcpy(s.h_in, rgba, in_bytes);
+        src_ptr = s.h_in;
+    }
+    TXP_CUDA(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
+    uint32_t* base = reinterpret_cast<uint32_t*>(s.d_in);
+    for (int l = 1; l < n; ++l) {
+        const uint32_t dw = src.lw[l], dh = src.lh[l];
+        mip_downsample_kernel<<<(dw * dh + 255) / 256, 256, 0, s.stream>>>(base + src.loff[l - 1], src.lw[l - 1], src.lh[l - 1], base + src.loff[l], dw, dh);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    TXP_CUDA(cudaGetLastError());
+    src.rgba = s.d_in; src.masks = nullptr; src.w = (uint32_t)w; src.h = (uint32_t)h; src.bw = (uint32_t)txp_num_blocks(w);
+    src.vec_ok = 1;                                       // cudaMalloc base; per-level width checked in locate_block
+    if ((rc = launch_encode(format, src, p, s.d_out, s.stream)) != TXP_OK) return rc;
+    if (dma_direct(output)) {
+        TXP_CUDA(cudaMemcpyAsync(output, s.d_out, total_out, cudaMemcpyDefault, s.stream));
+    } else {
+        if ((rc = grow_pinned(&s.h_out, &s.h_out_cap, total_out)) != TXP_OK) return rc;
+        TXP_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, total_out, cudaMemcpyDeviceToHost, s.stream));
+        s.user_out = output; s.user_out_bytes = total_out;
+    }
+    TXP_CUDA(cudaEventRecord(s.done, s.stream));
+    s.busy = true;
     return TXP_OK;
 }
 
@@ -488,7 +565,7 @@ int txp_compress_blocks(int format, const uint8_t* rgba_blocks, const uint32_t* 
     TXP_CUDA(cudaMemcpyAsync(s.d_in, rgba_blocks, n * 64, cudaMemcpyDefault, s.stream));
     TXP_CUDA(cudaMemcpyAsync(c->d_masks, masks, n * 4, cudaMemcpyDefault, s.stream));
     BlockSource src;
-    src.rgba = s.d_in; src.masks = c->d_masks; src.w = 0; src.h = 0; src.bw = 1; src.nblocks = n; src.vec_ok = 1;
+    src.rgba = s.d_in; src.masks = c->d_masks; src.w = 0; src.h = 0; src.bw = 1; src.nblocks = n; src.vec_ok = 1; src.nlevels = 1;
     if ((rc = launch_encode(format, src, params, s.d_out, s.stream)) != TXP_OK) return rc;
     TXP_CUDA(cudaMemcpyAsync(output, s.d_out, n * bs, cudaMemcpyDefault, s.stream));
     TXP_CUDA(cudaStreamSynchronize(s.stream));
@@ -525,6 +602,78 @@ int txp_decompress_block(int format, const uint8_t* block, size_t block_len, uin
     if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
     if (block_len < (size_t)block_bytes(format)) return fail(TXP_ERR_BUFFER_TOO_SMALL, "block shorter than block_size");
     return txp_decompress_blocks(format, block, 1, output);
+}
+
+
+int txp_mip_levels(size_t width, size_t height) {
+    if (width == 0 || height == 0) return fail(TXP_ERR_DIMENSIONS, "zero dimension");
+    return mip_layout(0, width, height, nullptr, nullptr, nullptr);
+}
+
+size_t txp_mipchain_compressed_size(int format, size_t width, size_t height) {
+    size_t total = 0;
+    if (format < 0 || format > 4 || width == 0 || height == 0) return 0;
+    if (mip_layout(format, width, height, nullptr, nullptr, &total) < 0) return 0;
+    return total;
+}
+
+int txp_compress_mipchain(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height, const txp_params* params,
+                          uint8_t* output, size_t output_len) {
+    int rc;
+    if ((rc = check_params(format, params)) != TXP_OK) return rc;
+    if ((rc = check_dims(width, height)) != TXP_OK) return rc;
+    if (height == 0) return fail(TXP_ERR_DIMENSIONS, "height must be non-zero");
+    if (!rgba || !output) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    if (rgba_len < width * height * 4) return fail(TXP_ERR_BUFFER_TOO_SMALL, "rgba shorter than 4*width*height");
+    if (output_len < txp_mipchain_compressed_size(format, width, height)) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than the mip chain");
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    Slot& s = c->slots[0];
+    if ((rc = slot_wait(s)) != TXP_OK) return rc;
+    if ((rc = mipchain_enqueue(s, format, rgba, width, height, params, output)) != TXP_OK) return rc;
+    return slot_wait(s);
+}
+
+int txp_compress_batch_mips(int format, const uint8_t* const* rgba, const size_t* widths, const size_t* heights, size_t n_textures,
+                            const txp_params* params, uint8_t* const* outputs, int n_gpus) {
+    int rc;
+    if ((rc = check_params(format, params)) != TXP_OK) return rc;
+    if (n_textures == 0) return TXP_OK;
+    if (!rgba || !widths || !heights || !outputs) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    const int ndev = txp_device_count();
+    if (ndev < 0) return ndev;
+    if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
+    for (size_t t = 0; t < n_textures; ++t)
+        if (widths[t] == 0 || heights[t] == 0 || widths[t] > 0x3FFFFFFFull || heights[t] > 0x3FFFFFFFull)
+            return fail(TXP_ERR_DIMENSIONS, "bad texture dimension");
+    std::vector<int> rcs((size_t)n_gpus, TXP_OK);
+    std::vector<std::string> errs((size_t)n_gpus);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_gpus; ++g) {
+        workers.emplace_back([&, g]() {
+            int r = TXP_OK;
+            DeviceCtx* c = nullptr;
+            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            if (r == TXP_OK) {
+                std::lock_guard<std::mutex> lk(c->mu);
+                size_t k = 0;                              // texture t -> device t % n_gpus, slots round-robin so that
+                for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus, ++k) {   // copies overlap kernels
+                    Slot& s = c->slots[k % NSLOTS];
+                    if ((r = slot_wait(s)) != TXP_OK) break;
+                    r = mipchain_enqueue(s, format, rgba[t], widths[t], heights[t], params, outputs[t]);
+                }
+                for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
+            }
+            rcs[(size_t)g] = r;
+            if (r != TXP_OK) errs[(size_t)g] = t_last_error;
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int g = 0; g < n_gpus; ++g)
+        if (rcs[(size_t)g] != TXP_OK) return fail(rcs[(size_t)g], "gpu " + std::to_string(g) + ": " + errs[(size_t)g]);
+    return TXP_OK;
 }
 
 int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height, const txp_params* params,

@@ -108,5 +108,28 @@ def main():
         del img
 
 
+def mips_case(n_tex, n_gpus):
+    """BASELINE config 5 (scaled down): textures 1024^2 `smooth` + full mip chains, BC3 ClusterFit, end to end."""
+    import time
+    texs = [(synth.generate("smooth", 1024, 1024, 5_000_000 + t), 1024, 1024) for t in range(n_tex)]
+    pinned = [torch.from_numpy(t[0].reshape(-1)).pin_memory() for t in texs]
+    texs = [(p.numpy(), 1024, 1024) for p in pinned]
+    size = L.txp_mipchain_compressed_size(2, 1024, 1024)
+    outs_t = [torch.empty(size, dtype=torch.uint8).pin_memory() for _ in range(n_tex)]
+    outs = [o.numpy() for o in outs_t]
+    T.compress_batch_mips(T.Format.Bc3, texs, T.Params(), n_gpus=n_gpus, outputs=outs)      # warm-up
+    t0 = time.perf_counter()
+    T.compress_batch_mips(T.Format.Bc3, texs, T.Params(), n_gpus=n_gpus, outputs=outs)
+    dt = time.perf_counter() - t0
+    pix = n_tex * sum(w * h for w, h in T.mip_levels(1024, 1024))
+    print(json.dumps({"case": "bc3_cluster_batch_mips_e2e", "textures": n_tex, "n_gpus": n_gpus, "s": dt,
+                      "mpix_s": pix / dt / 1e6, "textures_per_s": n_tex / dt}), flush=True)
+
+
 if __name__ == "__main__":
+    if "--mips" in sys.argv:
+        i = sys.argv.index("--mips")
+        torch.cuda.set_device(0); T.set_device(0)
+        mips_case(int(sys.argv[i + 1]), int(sys.argv[i + 2]) if len(sys.argv) > i + 2 else 1)
+        sys.exit(0)
     main()
