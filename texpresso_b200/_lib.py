@@ -13,7 +13,7 @@ EXPORTS = [
     "txp_compress_block_masked", "txp_decompress_block", "txp_compress_blocks", "txp_decompress_blocks",
     "txp_compress_device", "txp_decompress_device", "txp_shard_rows", "txp_compress_multi", "txp_compress_batch",
     "txp_mip_levels", "txp_mipchain_compressed_size", "txp_compress_mipchain", "txp_compress_batch_mips",
-    "txp_device_count", "txp_set_device", "txp_last_error", "txp_kernel_launches", "txp_version",
+    "txp_device_count", "txp_set_device", "txp_last_error", "txp_kernel_launches", "txp_version", "txp_debug_set",
 ]
 
 
@@ -64,6 +64,7 @@ def load():
         "txp_last_error": (ctypes.c_char_p, []),
         "txp_kernel_launches": (ctypes.c_uint64, []),
         "txp_version": (ctypes.c_char_p, []),
+        "txp_debug_set": (ci, [ci, ci]),
     }
     for name in EXPORTS:
         fn = getattr(L, name)          # AttributeError if the library does not export it

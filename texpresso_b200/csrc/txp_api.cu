@@ -19,6 +19,7 @@
 #include "txp_alpha.cuh"
 #include "txp_colour.cuh"
 #include "txp_range.cuh"
+#include "txp_cluster_setup.cuh"
 #include "txp_decode.cuh"
 
 namespace txp {
@@ -57,10 +58,47 @@ __global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour
     uint2 alpha_half = make_uint2(0u, 0u);
     if (FMT == BC2) alpha_half = warp_alpha_bc2(pix >> 24, valid, lane);          // lib.rs:198
     if (FMT == BC3) alpha_half = warp_alpha_bc3(pix >> 24, valid, lane);          // lib.rs:199
-    const uint2 colour = colour_block<FMT == BC1>(pix, valid, prm, scratch + warp, tab3, tab4, lane);
+    const uint2 colour = colour_block<FMT == BC1, false>(pix, valid, prm, scratch + warp, tab3, tab4, lane);
     if (lane == 0) {
         if (FMT == BC1) reinterpret_cast<uint2*>(out)[b] = colour;
         else reinterpret_cast<uint4*>(out)[b] = make_uint4(alpha_half.x, alpha_half.y, colour.x, colour.y);   // lib.rs:213
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ClusterFit search kernel ("K2"): one warp per block that cluster_setup_kernel flagged for the partition search.
+// Writes only the colour half; the alpha half of BC2/BC3 was written by the setup kernel.
+// ---------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour_search_kernel(const BlockSource src, const EncodeParams prm,
+                                                                                               const uint4* __restrict__ setup,
+                                                                                               uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t b = (uint64_t)blockIdx.x * COLOUR_WARPS + warp;
+    if (b >= src.nblocks) return;
+    const uint4 su = __ldg(setup + b);
+    if (!(su.z & SETUP_SEARCH)) return;                   // finished by the setup kernel (0 or 1 points)
+    uint32_t pix = 0;
+    bool valid = false;
+    if (lane < 16) {
+        if (src.masks) {
+            pix = __ldg(reinterpret_cast<const uint32_t*>(src.rgba) + b * 16 + lane);
+            valid = (__ldg(src.masks + b) >> lane) & 1u;
+        } else {
+            const BlockPos bp = locate_block(src, (uint32_t)b);
+            const uint32_t sx = bp.x0 + (lane & 3), sy = bp.y0 + (lane >> 2);
+            valid = sx < bp.w && sy < bp.h;
+            if (valid) pix = __ldg(reinterpret_cast<const uint32_t*>(bp.base) + (size_t)sy * bp.w + sx);
+        }
+    }
+    const unsigned long long ow0 = (unsigned long long)su.x | ((unsigned long long)su.y << 32);
+    const uint2 colour = colour_block<FMT == BC1, true>(pix, valid, prm, scratch + warp, g_tab3, g_tab4, lane, ow0,
+                                                         (su.z & SETUP_DEGENERATE) != 0);
+    if (lane == 0) {
+        uint2* out2 = reinterpret_cast<uint2*>(out);
+        if (FMT == BC1) out2[b] = colour; else out2[2 * b + 1] = colour;                // lib.rs:213
     }
 }
 
@@ -87,6 +125,8 @@ __global__ void __launch_bounds__(256) mip_downsample_kernel(const uint32_t* __r
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string t_last_error;
 static std::atomic<uint64_t> g_launches{0};
+// tuning knob: 1 = single fused ClusterFit kernel, 0 = setup kernel + search kernel (default); TXP_COLOUR_VARIANT=fused
+static std::atomic<int> g_colour_fused{[] { const char* v = getenv("TXP_COLOUR_VARIANT"); return (v && std::string(v) == "fused") ? 1 : 0; }()};
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
 
@@ -154,6 +194,9 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
+        TXP_CUDA(cudaFuncSetAttribute(colour_search_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
+        TXP_CUDA(cudaFuncSetAttribute(colour_search_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
+        TXP_CUDA(cudaFuncSetAttribute(colour_search_kernel<BC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         for (Slot& s : c.slots) {
             TXP_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             TXP_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -257,9 +300,25 @@ static int launch_encode(int format, const BlockSource& src, const txp_params* p
     } else {
         const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
         const unsigned threads = COLOUR_WARPS * 32;
-        if (format == BC1) colour_encode_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
-        else if (format == BC2) colour_encode_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
-        else colour_encode_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
+        if (g_colour_fused.load(std::memory_order_relaxed)) {                                      // single-kernel variant kept for A/B measurements
+            if (format == BC1) colour_encode_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
+            else if (format == BC2) colour_encode_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
+            else colour_encode_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
+        } else {
+            // K1 (thread per block: alpha half, colour set, principal axis, first ordering) -> K2 (warp per block: search)
+            uint4* setup = nullptr;
+            TXP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&setup), (size_t)src.nblocks * sizeof(uint4), st));
+            const unsigned g1 = (unsigned)((src.nblocks + 127) / 128);
+            if (format == BC1) cluster_setup_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup);
+            else if (format == BC2) cluster_setup_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup);
+            else cluster_setup_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup);
+            if (format == BC1) colour_search_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
+            else if (format == BC2) colour_search_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
+            else colour_search_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            TXP_CUDA(cudaGetLastError());
+            TXP_CUDA(cudaFreeAsync(setup, st));
+        }
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     TXP_CUDA(cudaGetLastError());
@@ -452,6 +511,11 @@ size_t txp_compressed_size(int format, size_t width, size_t height) {
 const char* txp_last_error(void) { return t_last_error.c_str(); }
 uint64_t txp_kernel_launches(void) { return g_launches.load(); }
 const char* txp_version(void) { return "texpresso_b200 0.1 (sm_100a)"; }
+
+int txp_debug_set(int key, int value) {
+    if (key == 0) { g_colour_fused.store(value ? 1 : 0); return TXP_OK; }
+    return fail(TXP_ERR_ARGUMENT, "unknown debug key");
+}
 
 int txp_device_count(void) {
     int n = 0;

@@ -19,7 +19,7 @@
 #include "txp_common.cuh"
 
 #ifndef TXP_SEARCH_UNROLL
-#define TXP_SEARCH_UNROLL 2          // candidates per lane and loop trip in the partition search (A/B: profiles/README.md)
+#define TXP_SEARCH_UNROLL 1          // candidates per lane and loop trip in the partition search (interleaved A/B: profiles/README.md)
 #endif
 #define TXP_PRAGMA_(x) _Pragma(#x)
 #define TXP_UNROLL(n) TXP_PRAGMA_(unroll n)
@@ -197,8 +197,13 @@ __device__ __forceinline__ uint32_t pixel_indices(const SetInfo& s, const int po
 // ---------------------------------------------------------------------------------------------------
 // ClusterFit pass (cluster.rs:152-274 for THREE, :276-417 otherwise).  Updates best_error/best_block.
 // ---------------------------------------------------------------------------------------------------
-template <bool THREE, bool ITERATE>
+// USE_OW0: the ordering of iteration 0 (principal axis) comes from the setup kernel as `ow0`.
+// table_ow / table_valid: ordering for which ws->PW / ws->S currently hold the range sums, so that BC1's 3- and
+// 4-colour passes (both start from the principal axis, cluster.rs:172 / :299) build them once.
+template <bool THREE, bool ITERATE, bool USE_OW0>
 __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const float3 principle,
+                             const unsigned long long ow0, const bool ow0_degenerate,
+                             unsigned long long& table_ow, bool& table_valid,
                              WarpScratch* ws, const uint32_t* tab, const int lane,
                              float& best_error, uint2& best_block) {
     const int count = s.count;
@@ -217,28 +222,42 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const fl
 #pragma unroll 1
     for (int it = 0; it < niter; ++it) {
         // ---- construct_ordering (cluster.rs:78-136) ------------------------------------------------
-        const float dp = lane < count ? add(add(mul(s.px, axx), mul(s.py, axy)), mul(s.pz, axz)) : FLT_MAX;
-        const int idv = lane < count ? lane : 0;
-        // fcmp (cluster.rs:90-97): non-finite values compare Equal to each other and Greater than finite.
-        const uint32_t bits = __float_as_uint(dp);
-        int sk;
-        if ((bits & 0x7F800000u) == 0x7F800000u) sk = 0x7FFFFFFF;
-        else sk = (bits & 0x80000000u) ? -(int)(bits & 0x7FFFFFFFu) : (int)bits;
-        if (lane < 16) ws->keys[lane] = sk;
-        __syncwarp();
-        int rank = 0;                                    // stable rank == insertion sort position
+        unsigned long long ow;
+        int rank;
+        bool degenerate;
+        if (USE_OW0 && it == 0) {
+            ow = ow0;
+            degenerate = ow0_degenerate;
+            // rank of point `lane` = its position in the ordering (inverse permutation through shared memory)
+            if (lane < count) ws->keys[(ow >> (4 * lane)) & 15ull] = lane;
+            __syncwarp();
+            rank = lane < 16 ? ws->keys[lane] : 0;
+            __syncwarp();
+        } else {
+            const float dp = lane < count ? add(add(mul(s.px, axx), mul(s.py, axy)), mul(s.pz, axz)) : FLT_MAX;
+            const int idv = lane < count ? lane : 0;
+            // fcmp (cluster.rs:90-97): non-finite values compare Equal to each other and Greater than finite.
+            const uint32_t bits = __float_as_uint(dp);
+            int sk;
+            if ((bits & 0x7F800000u) == 0x7F800000u) sk = 0x7FFFFFFF;
+            else sk = (bits & 0x80000000u) ? -(int)(bits & 0x7FFFFFFFu) : (int)bits;
+            if (lane < 16) ws->keys[lane] = sk;
+            __syncwarp();
+            rank = 0;                                    // stable rank == insertion sort position
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int kj = ws->keys[j];
-            rank += (kj < sk || (kj == sk && j < lane)) ? 1 : 0;
+            for (int j = 0; j < 16; ++j) {
+                const int kj = ws->keys[j];
+                rank += (kj < sk || (kj == sk && j < lane)) ? 1 : 0;
+            }
+            uint32_t lo = 0, hi = 0;
+            if (lane < 16) {
+                if (rank < 8) lo = (uint32_t)idv << (4 * rank); else hi = (uint32_t)idv << (4 * (rank - 8));
+            }
+            lo = __reduce_or_sync(FULL, lo);
+            hi = __reduce_or_sync(FULL, hi);
+            ow = (unsigned long long)lo | ((unsigned long long)hi << 32);
+            degenerate = __any_sync(FULL, lane < count && sk == 0x7FFFFFFF);
         }
-        uint32_t lo = 0, hi = 0;
-        if (lane < 16) {
-            if (rank < 8) lo = (uint32_t)idv << (4 * rank); else hi = (uint32_t)idv << (4 * (rank - 8));
-        }
-        lo = __reduce_or_sync(FULL, lo);
-        hi = __reduce_or_sync(FULL, hi);
-        const unsigned long long ow = (unsigned long long)lo | ((unsigned long long)hi << 32);
         if (ITERATE) {
             bool dup = false;                            // cluster.rs:108-120
             for (int p = 0; p < it; ++p) dup |= (ws->seen[p] == ow);
@@ -246,12 +265,13 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const fl
             __syncwarp();
             if (lane == 0) ws->seen[it] = ow;
         }
-        // ordered weighted points: PW[m] = UW[order[m]]  (cluster.rs:126-132)
-        if (lane < count) ws->PW[lane] = ws->UW[(ow >> (4 * lane)) & 15ull];
-        if (lane <= count) ws->S[lane * 17 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
-        // ---- range-sum table: row `lane` accumulated left to right -----------------------------------
-        {
+        if (!(table_valid && table_ow == ow)) {
+            // ordered weighted points: PW[m] = UW[order[m]]  (cluster.rs:126-132)
+            __syncwarp();
+            if (lane < count) ws->PW[lane] = ws->UW[(ow >> (4 * lane)) & 15ull];
+            if (lane <= count) ws->S[lane * 17 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            // ---- range-sum table: row `lane` accumulated left to right -------------------------------
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int b = 0; b < count; ++b) {
                 const float4 v = ws->PW[b];
@@ -260,8 +280,9 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const fl
                     ws->S[lane * 17 + b + 1] = acc;
                 }
             }
+            __syncwarp();
+            table_ow = ow; table_valid = true;
         }
-        __syncwarp();
         const float4 xsum = ws->S[count];                // == xsum_wsum (cluster.rs:125-133)
         const f32x2 xs_xy = pk(xsum.x, xsum.y), xs_zw = pk(xsum.z, xsum.w);
 
@@ -290,7 +311,7 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const fl
             best_E = Ewin;
             best_ow = ow;
             best_rank = rank;
-            best_degenerate = __any_sync(FULL, lane < count && sk == 0x7FFFFFFF);
+            best_degenerate = degenerate;
 #pragma unroll
             for (int c = 0; c < 3; ++c) { bka[c] = sol.ka[c]; bkb[c] = sol.kb[c]; }
             bsx = sol.ax; bsy = sol.ay; bsz = sol.az; bex = sol.bx; bey = sol.by; bez = sol.bz;
@@ -454,9 +475,12 @@ __device__ uint2 single_fit(const SetInfo& s, const uint32_t rgb, const int lane
 // Colour half of one block: ColourSet (colourset.rs:35-112) + dispatch (lib.rs:208-231).
 // `pix`/`valid` are meaningful for lanes 0..15; result is uniform across the warp.
 // ---------------------------------------------------------------------------------------------------
-template <bool IS_BC1>
+// HAVE_SETUP: the block went through cluster_setup_kernel (txp_cluster_setup.cuh): it has >= 2 points, and the
+// principal-axis ordering `ow0` is given, so covariance / power iteration / first sort are skipped here.
+template <bool IS_BC1, bool HAVE_SETUP>
 __device__ uint2 colour_block(const uint32_t pix, const bool valid, const EncodeParams& prm,
-                              WarpScratch* ws, const uint32_t* tab3, const uint32_t* tab4, const int lane) {
+                              WarpScratch* ws, const uint32_t* tab3, const uint32_t* tab4, const int lane,
+                              const unsigned long long ow0 = 0, const bool ow0_degenerate = false) {
     const uint32_t rgb = pix & 0x00FFFFFFu, alpha = pix >> 24;
     const bool punched = IS_BC1 && valid && alpha < 128u;                         // colourset.rs:54
     const bool active = valid && !punched;
@@ -497,63 +521,71 @@ __device__ uint2 colour_block(const uint32_t pix, const bool valid, const Encode
     if (lane < s.count) ws->UW[lane] = make_float4(mul(pt.x, pt.w), mul(pt.y, pt.w), mul(pt.z, pt.w), mul(1.0f, pt.w));
     __syncwarp();
 
-    // ---- Sym3x3::weighted_covariance (math.rs:44-73), sums in set order -----------------------------
-    float acc = 0.0f;
-    if (lane < 4) {
-        const float* uw = reinterpret_cast<const float*>(ws->UW);
-        for (int k = 0; k < s.count; ++k) acc = add(acc, uw[4 * k + lane]);
-    }
-    const float total = __shfl_sync(FULL, acc, 3);
-    float cx = __shfl_sync(FULL, acc, 0), cy = __shfl_sync(FULL, acc, 1), cz = __shfl_sync(FULL, acc, 2);
-    if (total > FLT_EPSILON) { cx = fdiv(cx, total); cy = fdiv(cy, total); cz = fdiv(cz, total); }
-    if (lane < s.count) {
-        const float ax = sub(pt.x, cx), ay = sub(pt.y, cy), az = sub(pt.z, cz);
-        const float bx = mul(ax, pt.w), by = mul(ay, pt.w), bz = mul(az, pt.w);
-        float* pr = ws->prod[lane];
-        pr[0] = mul(ax, bx); pr[1] = mul(ax, by); pr[2] = mul(ax, bz);
-        pr[3] = mul(ay, by); pr[4] = mul(ay, bz); pr[5] = mul(az, bz);
-    }
-    __syncwarp();
-    acc = 0.0f;
-    if (lane < 6) for (int k = 0; k < s.count; ++k) acc = add(acc, ws->prod[k][lane]);
-    const float m0 = __shfl_sync(FULL, acc, 0), m1 = __shfl_sync(FULL, acc, 1), m2 = __shfl_sync(FULL, acc, 2);
-    const float m3 = __shfl_sync(FULL, acc, 3), m4 = __shfl_sync(FULL, acc, 4), m5 = __shfl_sync(FULL, acc, 5);
+    float3 principle = make_float3(0.f, 0.f, 0.f);
+    if (!HAVE_SETUP) {
+        // ---- Sym3x3::weighted_covariance (math.rs:44-73), sums in set order -----------------------------
+        float acc = 0.0f;
+        if (lane < 4) {
+            const float* uw = reinterpret_cast<const float*>(ws->UW);
+            for (int k = 0; k < s.count; ++k) acc = add(acc, uw[4 * k + lane]);
+        }
+        const float total = __shfl_sync(FULL, acc, 3);
+        float cx = __shfl_sync(FULL, acc, 0), cy = __shfl_sync(FULL, acc, 1), cz = __shfl_sync(FULL, acc, 2);
+        if (total > FLT_EPSILON) { cx = fdiv(cx, total); cy = fdiv(cy, total); cz = fdiv(cz, total); }
+        if (lane < s.count) {
+            const float ax = sub(pt.x, cx), ay = sub(pt.y, cy), az = sub(pt.z, cz);
+            const float bx = mul(ax, pt.w), by = mul(ay, pt.w), bz = mul(az, pt.w);
+            float* pr = ws->prod[lane];
+            pr[0] = mul(ax, bx); pr[1] = mul(ax, by); pr[2] = mul(ax, bz);
+            pr[3] = mul(ay, by); pr[4] = mul(ay, bz); pr[5] = mul(az, bz);
+        }
+        __syncwarp();
+        acc = 0.0f;
+        if (lane < 6) for (int k = 0; k < s.count; ++k) acc = add(acc, ws->prod[k][lane]);
+        const float m0 = __shfl_sync(FULL, acc, 0), m1 = __shfl_sync(FULL, acc, 1), m2 = __shfl_sync(FULL, acc, 2);
+        const float m3 = __shfl_sync(FULL, acc, 3), m4 = __shfl_sync(FULL, acc, 4), m5 = __shfl_sync(FULL, acc, 5);
 
-    // ---- principle_component (math.rs:75-97): 8 power iterations, uniform ---------------------------
-    float vx = 1.0f, vy = 1.0f, vz = 1.0f;
-#pragma unroll 1
-    for (int it = 0; it < 8; ++it) {
-        const float wx = add(mul(m2, vz), add(mul(m1, vy), mul(m0, vx)));
-        const float wy = add(mul(m4, vz), add(mul(m3, vy), mul(m1, vx)));
-        const float wz = add(mul(m5, vz), add(mul(m4, vy), mul(m2, vx)));
-        const float a = fmaxf(wx, fmaxf(wy, wz));
-        const float ra = rcp(a);
-        vx = mul(wx, ra); vy = mul(wy, ra); vz = mul(wz, ra);
-    }
-    const float3 principle = make_float3(vx, vy, vz);
+        // ---- principle_component (math.rs:75-97): 8 power iterations, uniform ---------------------------
+        float vx = 1.0f, vy = 1.0f, vz = 1.0f;
+    #pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            const float wx = add(mul(m2, vz), add(mul(m1, vy), mul(m0, vx)));
+            const float wy = add(mul(m4, vz), add(mul(m3, vy), mul(m1, vx)));
+            const float wz = add(mul(m5, vz), add(mul(m4, vy), mul(m2, vx)));
+            const float a = fmaxf(wx, fmaxf(wy, wz));
+            const float ra = rcp(a);
+            vx = mul(wx, ra); vy = mul(wy, ra); vz = mul(wz, ra);
+        }
+        principle = make_float3(vx, vy, vz);
 
-    if (prm.algorithm == RANGE_FIT) return range_fit<IS_BC1>(s, prm, principle, lane);
+        if (prm.algorithm == RANGE_FIT) return range_fit<IS_BC1>(s, prm, principle, lane);
+
+    }
 
     // ---- ClusterFit (cluster.rs:49-76 + colourfit.rs:48-59) ----------------------------------------
     float best_error = FLT_MAX;
     uint2 block = make_uint2(0u, 0u);
+    unsigned long long table_ow = 0;
+    bool table_valid = false;
+#define TXP_PASS(THREE, ITER, TAB) cluster_pass<THREE, ITER, HAVE_SETUP>(s, prm, principle, ow0, ow0_degenerate, table_ow, table_valid, ws, TAB, lane, best_error, block)
     if (prm.algorithm == ITERATIVE_CLUSTER_FIT) {
         if (IS_BC1) {
-            cluster_pass<true, true>(s, prm, principle, ws, tab3, lane, best_error, block);
+            TXP_PASS(true, true, tab3);
             __syncwarp();
-            if (!s.transparent) cluster_pass<false, true>(s, prm, principle, ws, tab4, lane, best_error, block);
+            if (!s.transparent) TXP_PASS(false, true, tab4);
         } else {
-            cluster_pass<false, true>(s, prm, principle, ws, tab4, lane, best_error, block);
+            TXP_PASS(false, true, tab4);
         }
     } else {
         if (IS_BC1) {
-            cluster_pass<true, false>(s, prm, principle, ws, tab3, lane, best_error, block);
+            TXP_PASS(true, false, tab3);
             __syncwarp();
-            if (!s.transparent) cluster_pass<false, false>(s, prm, principle, ws, tab4, lane, best_error, block);
+            if (!s.transparent) TXP_PASS(false, false, tab4);
         } else {
-            cluster_pass<false, false>(s, prm, principle, ws, tab4, lane, best_error, block);
+            TXP_PASS(false, false, tab4);
         }
     }
+#undef TXP_PASS
     return block;
 }
 

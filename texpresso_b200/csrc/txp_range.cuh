@@ -84,32 +84,35 @@ __device__ __forceinline__ uint2 alpha_bc2_thread(const uint32_t px[16], const u
     return make_uint2(w[0], w[1]);
 }
 
-// Colour half of one block with Algorithm::RangeFit.  px: 16 RGBA words, mask: valid bits, lut: c/255 table.
+// ---- per-thread ColourSet (colourset.rs:35-112), shared by the RangeFit kernel and the ClusterFit setup kernel ----
+struct ThreadSet {
+    uint32_t active16;       // valid and not punched through
+    uint32_t new16;          // first occurrence of its RGB among the active pixels  (== the points of the set, in order)
+    bool transparent;        // BC1 punch-through present (colourset.rs:54-58)
+};
+
+// px[] is rewritten in place to comparison keys (RGB for active pixels, a unique value otherwise);
+// gw[i] = integer weight total of the group whose first pixel is i (1 per pixel, or alpha+1: exact sums)
 template <bool IS_BC1>
-__device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint32_t mask, const EncodeParams& prm,
-                                                     const float* __restrict__ lut) {
-    // ---- ColourSet (colourset.rs:35-112) ----------------------------------------------------------------
-    uint32_t active16 = 0, punched = 0;
-    uint32_t wgt[16];                                   // integer weight of pixel i: 1, or alpha+1 (exact sums)
+__device__ __forceinline__ ThreadSet thread_colourset(uint32_t px[16], const uint32_t mask, const bool alpha_weighted, uint32_t gw[16]) {
+    ThreadSet t;
+    t.active16 = 0;
+    uint32_t punched = 0;
+    uint32_t wgt[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const bool valid = (mask >> i) & 1u;
         const bool pt = IS_BC1 && valid && (px[i] >> 24) < 128u;                  // :54
         if (pt) punched |= 1u << i;
-        if (valid && !pt) active16 |= 1u << i;
-        wgt[i] = prm.alpha_weighted ? (px[i] >> 24) + 1u : 1u;
-        // key: RGB for active pixels, a unique value otherwise (never equal to anything)
+        if (valid && !pt) t.active16 |= 1u << i;
+        wgt[i] = alpha_weighted ? (px[i] >> 24) + 1u : 1u;
         px[i] = (valid && !pt) ? (px[i] & 0x00FFFFFFu) : (0x01000000u | (uint32_t)i);
+        gw[i] = wgt[i];
     }
-    const bool transparent = punched != 0;
-    if (active16 == 0)                                   // lib.rs:223, SURVEY Q14
-        return IS_BC1 ? make_uint2(0u, 0xFFFFFFFFu) : make_uint2(0u, 0u);
+    t.transparent = punched != 0;
     // exact-RGB duplicates (:84-88): pixel i is new iff no earlier pixel has its key; group weights are
     // accumulated on every earlier equal pixel (only the first one's total is used)
     uint32_t dup16 = 0;
-    uint32_t gw[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) gw[i] = wgt[i];
 #pragma unroll
     for (int i = 1; i < 16; ++i) {
         bool dup = false;
@@ -121,29 +124,26 @@ __device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint
         }
         if (dup) dup16 |= 1u << i;
     }
-    const uint32_t new16 = active16 & ~dup16;
-    if ((new16 & (new16 - 1u)) == 0u) {                  // exactly one distinct colour: lib.rs:217-222
-        uint32_t rgb = 0;                                // every active pixel carries it
-#pragma unroll
-        for (int i = 0; i < 16; ++i) if ((active16 >> i) & 1u) rgb |= px[i];
-        return single_fit_thread<IS_BC1>(rgb, active16, transparent);
-    }
+    t.new16 = t.active16 & ~dup16;
+    return t;
+}
 
-    // weights: sqrt of the group totals (:107-109); 0 for pixels that are not new
-    float w[16];
+// weights: sqrt of the group totals (colourset.rs:107-109); 0 for pixels that are not new
+__device__ __forceinline__ void thread_weights(const uint32_t gw[16], const uint32_t new16, const bool alpha_weighted, float w[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const bool is_new = (new16 >> i) & 1u;
         float t = 0.0f;
-        if (is_new) {
+        if ((new16 >> i) & 1u) {
             t = 1.0f;
-            if (gw[i] != 1u || prm.alpha_weighted)
-                t = __fsqrt_rn(prm.alpha_weighted ? mul((float)gw[i], 1.0f / 256.0f) : (float)gw[i]);
+            if (gw[i] != 1u || alpha_weighted)
+                t = __fsqrt_rn(alpha_weighted ? mul((float)gw[i], 1.0f / 256.0f) : (float)gw[i]);
         }
         w[i] = t;
     }
+}
 
-    // ---- Sym3x3::weighted_covariance (math.rs:44-73) --------------------------------------------------------
+// Sym3x3::weighted_covariance + principle_component (math.rs:44-97) over the 16 pixels with weight 0 for non-points
+__device__ __forceinline__ float3 thread_principal_axis(const uint32_t px[16], const float w[16], const float* __restrict__ lut) {
     float total = 0.0f, cx = 0.0f, cy = 0.0f, cz = 0.0f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -161,7 +161,6 @@ __device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint
         m0 = add(m0, mul(ax, bx)); m1 = add(m1, mul(ax, by)); m2 = add(m2, mul(ax, bz));
         m3 = add(m3, mul(ay, by)); m4 = add(m4, mul(ay, bz)); m5 = add(m5, mul(az, bz));
     }
-    // ---- principle_component (math.rs:75-97) ----------------------------------------------------------------
     float vx = 1.0f, vy = 1.0f, vz = 1.0f;
 #pragma unroll 1
     for (int it = 0; it < 8; ++it) {
@@ -171,6 +170,33 @@ __device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint
         const float ra = rcp(fmaxf(tx, fmaxf(ty, tz)));
         vx = mul(tx, ra); vy = mul(ty, ra); vz = mul(tz, ra);
     }
+    return make_float3(vx, vy, vz);
+}
+
+// the one colour of a single-colour block: every active pixel carries it
+__device__ __forceinline__ uint32_t thread_single_rgb(const uint32_t px[16], const uint32_t active16) {
+    uint32_t rgb = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) if ((active16 >> i) & 1u) rgb |= px[i];
+    return rgb;
+}
+
+// Colour half of one block with Algorithm::RangeFit.  px: 16 RGBA words, mask: valid bits, lut: c/255 table.
+template <bool IS_BC1>
+__device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint32_t mask, const EncodeParams& prm,
+                                                     const float* __restrict__ lut) {
+    uint32_t gw[16];
+    const ThreadSet ts = thread_colourset<IS_BC1>(px, mask, prm.alpha_weighted != 0, gw);
+    const uint32_t active16 = ts.active16, new16 = ts.new16;
+    const bool transparent = ts.transparent;
+    if (active16 == 0)                                   // lib.rs:223, SURVEY Q14
+        return IS_BC1 ? make_uint2(0u, 0xFFFFFFFFu) : make_uint2(0u, 0u);
+    if ((new16 & (new16 - 1u)) == 0u)                    // exactly one distinct colour: lib.rs:217-222
+        return single_fit_thread<IS_BC1>(thread_single_rgb(px, active16), active16, transparent);
+    float w[16];
+    thread_weights(gw, new16, prm.alpha_weighted != 0, w);
+    const float3 axis = thread_principal_axis(px, w, lut);
+    const float vx = axis.x, vy = axis.y, vz = axis.z;
     // ---- range.rs:67-86: first point starts both ends; strict < / else-if > over the following points ----------
     uint32_t ps = 0, pe = 0;
     float mn = 0.f, mx = 0.f;
