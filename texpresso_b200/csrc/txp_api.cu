@@ -159,6 +159,10 @@ struct DeviceCtx {
     Slot slots[NSLOTS];
     uint32_t* d_masks = nullptr;
     size_t masks_cap = 0;
+    // stream-ordered scratch (setup records between the ClusterFit kernels).  A private pool with an unlimited
+    // release threshold: the default pool hands memory back to the OS at every synchronisation, which would put a
+    // fresh device allocation inside every timed call.
+    cudaMemPool_t pool = nullptr;
 };
 
 static DeviceCtx g_ctx[MAX_DEVICES];
@@ -197,6 +201,16 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         TXP_CUDA(cudaFuncSetAttribute(colour_search_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_search_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_search_kernel<BC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
+        {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            TXP_CUDA(cudaMemPoolCreate(&c.pool, &props));
+            uint64_t keep = ~0ull;
+            TXP_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         for (Slot& s : c.slots) {
             TXP_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
             TXP_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -263,7 +277,7 @@ static EncodeParams to_device_params(const txp_params* p) {
 }
 
 // ---- kernel launchers -------------------------------------------------------------------------------
-static int launch_encode(int format, const BlockSource& src, const txp_params* p, uint8_t* d_out, cudaStream_t st) {
+static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, const txp_params* p, uint8_t* d_out, cudaStream_t st) {
     if (src.nblocks == 0) return TXP_OK;
     if (src.nblocks > 0x7FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^31-1 blocks in one launch");
     const EncodeParams e = to_device_params(p);
@@ -307,7 +321,7 @@ static int launch_encode(int format, const BlockSource& src, const txp_params* p
         } else {
             // K1 (thread per block: alpha half, colour set, principal axis, first ordering) -> K2 (warp per block: search)
             uint4* setup = nullptr;
-            TXP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&setup), (size_t)src.nblocks * sizeof(uint4), st));
+            TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&setup), (size_t)src.nblocks * sizeof(uint4), ctx.pool, st));
             const unsigned g1 = (unsigned)((src.nblocks + 127) / 128);
             if (format == BC1) cluster_setup_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup);
             else if (format == BC2) cluster_setup_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup);
@@ -402,7 +416,7 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
             TXP_CUDA(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
         }
         const BlockSource bsrc = image_source(s.d_in, w, h_sub, nblk);
-        if ((rc = launch_encode(format, bsrc, p, s.d_out, s.stream)) != TXP_OK) break;
+        if ((rc = launch_encode(c, format, bsrc, p, s.d_out, s.stream)) != TXP_OK) break;
         uint8_t* dst = out + (r - row0) * bw * bs;
         if (out_direct) {
             TXP_CUDA(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
@@ -453,7 +467,7 @@ static int mip_layout(int format, size_t w, size_t h, BlockSource* src, size_t* 
 }
 
 // enqueue H2D(level 0) -> mip kernels -> one encode launch -> D2H on slot s; the caller waits on the slot
-static int mipchain_enqueue(Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output) {
+static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output) {
     BlockSource src;
     size_t total_px = 0, total_out = 0;
     int n = mip_layout(format, w, h, &src, &total_px, &total_out);
@@ -478,7 +492,7 @@ static int mipchain_enqueue(Slot& s, int format, const uint8_t* rgba, size_t w, 
     TXP_CUDA(cudaGetLastError());
     src.rgba = s.d_in; src.masks = nullptr; src.w = (uint32_t)w; src.h = (uint32_t)h; src.bw = (uint32_t)txp_num_blocks(w);
     src.vec_ok = 1;                                       // cudaMalloc base; per-level width checked in locate_block
-    if ((rc = launch_encode(format, src, p, s.d_out, s.stream)) != TXP_OK) return rc;
+    if ((rc = launch_encode(ctx, format, src, p, s.d_out, s.stream)) != TXP_OK) return rc;
     if (dma_direct(output)) {
         TXP_CUDA(cudaMemcpyAsync(output, s.d_out, total_out, cudaMemcpyDefault, s.stream));
     } else {
@@ -548,7 +562,7 @@ int txp_compress_device(int format, const void* d_rgba, size_t width, size_t hei
     DeviceCtx* c;
     if ((rc = current_ctx(&c)) != TXP_OK) return rc;
     const BlockSource src = image_source(static_cast<const uint8_t*>(d_rgba), width, height, output_len / (size_t)block_bytes(format));
-    return launch_encode(format, src, params, static_cast<uint8_t*>(d_output), static_cast<cudaStream_t>(cuda_stream));
+    return launch_encode(*c, format, src, params, static_cast<uint8_t*>(d_output), static_cast<cudaStream_t>(cuda_stream));
 }
 
 int txp_decompress_device(int format, const void* d_data, size_t width, size_t height, void* d_output, size_t output_len,
@@ -630,7 +644,7 @@ int txp_compress_blocks(int format, const uint8_t* rgba_blocks, const uint32_t* 
     TXP_CUDA(cudaMemcpyAsync(c->d_masks, masks, n * 4, cudaMemcpyDefault, s.stream));
     BlockSource src;
     src.rgba = s.d_in; src.masks = c->d_masks; src.w = 0; src.h = 0; src.bw = 1; src.nblocks = n; src.vec_ok = 1; src.nlevels = 1;
-    if ((rc = launch_encode(format, src, params, s.d_out, s.stream)) != TXP_OK) return rc;
+    if ((rc = launch_encode(*c, format, src, params, s.d_out, s.stream)) != TXP_OK) return rc;
     TXP_CUDA(cudaMemcpyAsync(output, s.d_out, n * bs, cudaMemcpyDefault, s.stream));
     TXP_CUDA(cudaStreamSynchronize(s.stream));
     return TXP_OK;
@@ -695,7 +709,7 @@ int txp_compress_mipchain(int format, const uint8_t* rgba, size_t rgba_len, size
     std::lock_guard<std::mutex> lk(c->mu);
     Slot& s = c->slots[0];
     if ((rc = slot_wait(s)) != TXP_OK) return rc;
-    if ((rc = mipchain_enqueue(s, format, rgba, width, height, params, output)) != TXP_OK) return rc;
+    if ((rc = mipchain_enqueue(*c, s, format, rgba, width, height, params, output)) != TXP_OK) return rc;
     return slot_wait(s);
 }
 
@@ -726,7 +740,7 @@ int txp_compress_batch_mips(int format, const uint8_t* const* rgba, const size_t
                 for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus, ++k) {   // copies overlap kernels
                     Slot& s = c->slots[k % NSLOTS];
                     if ((r = slot_wait(s)) != TXP_OK) break;
-                    r = mipchain_enqueue(s, format, rgba[t], widths[t], heights[t], params, outputs[t]);
+                    r = mipchain_enqueue(*c, s, format, rgba[t], widths[t], heights[t], params, outputs[t]);
                 }
                 for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
             }
