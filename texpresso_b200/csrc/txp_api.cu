@@ -140,7 +140,8 @@ static int fail(int code, const std::string& msg) { t_last_error = msg; return c
 
 constexpr int MAX_DEVICES = 64;
 constexpr int NSLOTS = 3;
-constexpr size_t CHUNK_BYTES = 32u << 20;   // input bytes per pipeline stage
+constexpr size_t CHUNK_BYTES = 32u << 20;       // largest input chunk per pipeline stage
+constexpr size_t MIN_CHUNK_BYTES = 2u << 20;    // smallest chunk worth a separate launch + copy
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -388,7 +389,11 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
                               uint8_t* out, size_t row0, size_t row1, uint64_t blocks_in_range) {
     const size_t bs = (size_t)block_bytes(format), bw = (w + 3) / 4;
     const bool in_direct = dma_direct(rgba), out_direct = dma_direct(out);
-    size_t rows_per_chunk = CHUNK_BYTES / (16 * w);
+    // at least ~6 chunks per call so that H2D, kernels and D2H of neighbouring chunks overlap (small shards at 8 ranks)
+    size_t chunk_bytes = (row1 - row0) * 16 * w / 6;
+    if (chunk_bytes > CHUNK_BYTES) chunk_bytes = CHUNK_BYTES;
+    if (chunk_bytes < MIN_CHUNK_BYTES) chunk_bytes = MIN_CHUNK_BYTES;
+    size_t rows_per_chunk = chunk_bytes / (16 * w);
     if (rows_per_chunk == 0) rows_per_chunk = 1;
     int rc = TXP_OK;
     size_t chunk = 0;
