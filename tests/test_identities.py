@@ -73,3 +73,44 @@ def test_division_free_alpha_interpolants():
                 assert ((5 - i) * lo + i * hi) // 5 == lo + ((i * 205 * (hi - lo)) >> 10)
             for i in range(1, 7):
                 assert ((7 - i) * lo + i * hi) // 7 == lo + ((i * 9363 * (hi - lo)) >> 16)
+
+
+def _byte_perm(a, b, s):
+    """CUDA __byte_perm / PRMT (default mode)."""
+    src = [(a >> (8 * i)) & 255 for i in range(4)] + [(b >> (8 * i)) & 255 for i in range(4)]
+    out = 0
+    for i in range(4):
+        n = (s >> (4 * i)) & 0xF
+        v = src[n & 7]
+        if n & 8:
+            v = 0xFF if v & 0x80 else 0
+        out |= v << (8 * i)
+    return out
+
+
+def test_decoder_prmt_selectors():
+    # txp_decode.cuh: index spreaders and the plane -> pixel transpose selectors
+    def spread2to4(x):
+        y = (x | (x << 4)) & 0x0F0F
+        return (y | (y << 2)) & 0x3333
+
+    def spread3to4(x):
+        y = (x & 0x3F) | ((x & 0xFC0) << 2)
+        return (y & 0x0707) | ((y & 0x3838) << 1)
+
+    for x in range(256):
+        assert [(spread2to4(x) >> (4 * i)) & 0xF for i in range(4)] == [(x >> (2 * i)) & 3 for i in range(4)]
+    for x in range(4096):
+        assert [(spread3to4(x) >> (4 * i)) & 0xF for i in range(4)] == [(x >> (3 * i)) & 7 for i in range(4)]
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        planes = [int(v) for v in rng.integers(0, 1 << 32, 4)]
+        x = int(rng.integers(0, 256))
+        sel = spread2to4(x)
+        r4, g4, b4, a4 = [_byte_perm(p, 0, sel) for p in planes]
+        rg_lo, rg_hi = _byte_perm(r4, g4, 0x5140), _byte_perm(r4, g4, 0x7362)
+        ba_lo, ba_hi = _byte_perm(b4, a4, 0x5140), _byte_perm(b4, a4, 0x7362)
+        px = [_byte_perm(rg_lo, ba_lo, 0x5410), _byte_perm(rg_lo, ba_lo, 0x7632), _byte_perm(rg_hi, ba_hi, 0x5410), _byte_perm(rg_hi, ba_hi, 0x7632)]
+        for k in range(4):
+            idx = (x >> (2 * k)) & 3
+            assert px[k] == sum(((planes[c] >> (8 * idx)) & 255) << (8 * c) for c in range(4))

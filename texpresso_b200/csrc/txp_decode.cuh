@@ -15,27 +15,40 @@ __device__ __forceinline__ uint32_t unpack_565(const uint32_t v) {
     return ((r << 3) | (r >> 2)) | (((g << 2) | (g >> 4)) << 8) | (((b << 3) | (b >> 2)) << 16) | 0xFF000000u;
 }
 
-// colourblock.rs:116-169
+// 8 bits holding four 2-bit indices -> PRMT selector with the indices in its four nibbles
+__device__ __forceinline__ uint32_t spread2to4(const uint32_t x) {
+    const uint32_t y = (x | (x << 4)) & 0x0F0Fu;          // two fields per byte
+    return (y | (y << 2)) & 0x3333u;                      // one field per nibble
+}
+
+// colourblock.rs:116-169.  The four codes are held as channel planes (byte k of plane c = channel c of code k), so
+// one PRMT (a 4-entry byte LUT indexed by the selector nibbles) decodes a channel for the four pixels of a row; a
+// two-stage PRMT transpose then interleaves the planes into RGBA words.
 __device__ __forceinline__ void decode_colour(const uint2 blk, const bool is_bc1, uint32_t px[16]) {
     const uint32_t a = blk.x & 0xFFFFu, b = blk.x >> 16;
-    uint32_t codes[4];
-    codes[0] = unpack_565(a);
-    codes[1] = unpack_565(b);
-    uint32_t c2 = 0, c3 = 0;
+    const uint32_t e0 = unpack_565(a), e1 = unpack_565(b);
+    const bool three = is_bc1 && a <= b;
+    uint32_t plane[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const uint32_t c = (codes[0] >> (8 * ch)) & 255u, d = (codes[1] >> (8 * ch)) & 255u;
-        if (is_bc1 && a <= b) {
-            c2 |= ((c + d) / 2u) << (8 * ch);
-        } else {
-            c2 |= ((2u * c + d) / 3u) << (8 * ch);
-            c3 |= ((c + 2u * d) / 3u) << (8 * ch);
-        }
+        const uint32_t c = (e0 >> (8 * ch)) & 255u, d = (e1 >> (8 * ch)) & 255u;
+        const uint32_t c2 = three ? (c + d) / 2u : (2u * c + d) / 3u;
+        const uint32_t c3 = three ? 0u : (c + 2u * d) / 3u;
+        plane[ch] = c | (d << 8) | (c2 << 16) | (c3 << 24);
     }
-    codes[2] = c2 | 0xFF000000u;
-    codes[3] = (is_bc1 && a <= b) ? 0u : (c3 | 0xFF000000u);
+    const uint32_t plane_a = three ? 0x00FFFFFFu : 0xFFFFFFFFu;   // alpha 255, except code 3 of the 3-colour mode
 #pragma unroll
-    for (int i = 0; i < 16; ++i) px[i] = codes[(blk.y >> (2 * i)) & 3u];
+    for (int row = 0; row < 4; ++row) {
+        const uint32_t sel = spread2to4((blk.y >> (8 * row)) & 255u);
+        const uint32_t r4 = __byte_perm(plane[0], 0, sel), g4 = __byte_perm(plane[1], 0, sel);
+        const uint32_t b4 = __byte_perm(plane[2], 0, sel), a4 = __byte_perm(plane_a, 0, sel);
+        const uint32_t rg_lo = __byte_perm(r4, g4, 0x5140), rg_hi = __byte_perm(r4, g4, 0x7362);
+        const uint32_t ba_lo = __byte_perm(b4, a4, 0x5140), ba_hi = __byte_perm(b4, a4, 0x7362);
+        px[4 * row + 0] = __byte_perm(rg_lo, ba_lo, 0x5410);
+        px[4 * row + 1] = __byte_perm(rg_lo, ba_lo, 0x7632);
+        px[4 * row + 2] = __byte_perm(rg_hi, ba_hi, 0x5410);
+        px[4 * row + 3] = __byte_perm(rg_hi, ba_hi, 0x7632);
+    }
 }
 
 // 12 bits holding four 3-bit indices -> PRMT selector with the indices in its four nibbles
@@ -74,13 +87,15 @@ __device__ __forceinline__ void decode_alpha3(const uint2 blk, const int channel
     }
 }
 
-// alpha.rs:53-68
+// alpha.rs:53-68: nibble n -> n | n<<4 (= 17 n), four pixels per step
 __device__ __forceinline__ void decode_alpha2(const uint2 blk, uint32_t px[16]) {
-    const unsigned long long bits = ((unsigned long long)blk.y << 32) | blk.x;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t n = (uint32_t)(bits >> (4 * i)) & 15u;
-        px[i] = (px[i] & 0x00FFFFFFu) | ((n | (n << 4)) << 24);
+    for (int row = 0; row < 4; ++row) {
+        const uint32_t n4 = ((row < 2 ? blk.x : blk.y) >> (16 * (row & 1))) & 0xFFFFu;
+        const uint32_t y = (n4 & 0x00FFu) | ((n4 & 0xFF00u) << 8);            // two nibbles in bytes 0 and 2
+        const uint32_t four = ((y | (y << 4)) & 0x0F0F0F0Fu) * 17u;            // one nibble per byte, expanded to 8 bits
+#pragma unroll
+        for (int k = 0; k < 4; ++k) px[4 * row + k] = __byte_perm(px[4 * row + k], four, 0x0210u | ((4u + k) << 12));
     }
 }
 
