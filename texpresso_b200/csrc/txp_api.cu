@@ -28,7 +28,7 @@ namespace txp {
 // BC1/BC2/BC3 encoder kernel: one warp per block (see txp_colour.cuh)
 // ---------------------------------------------------------------------------------------------------
 #ifndef TXP_COLOUR_MIN_CTAS
-#define TXP_COLOUR_MIN_CTAS 4
+#define TXP_COLOUR_MIN_CTAS 8        // 8 CTAs x 4 warps x 64 registers = 32 warps per SM
 #endif
 template <int FMT>
 __global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour_encode_kernel(const BlockSource src, const EncodeParams prm,
