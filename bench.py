@@ -275,8 +275,10 @@ def run_ours(args):
             "metric": METRIC if not iterative else "BC1 IterativeClusterFit Mpix/s (8192^2 synthetic RGBA, BASELINE config 3)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BC1+BC3 ClusterFit, 8192x8192 synthetic RGBA (BC1: noise_opaque, BC3: noise_alpha, seed 3), "
-                                   "PERCEPTUAL weights, sharded by block rows",
+            "config": {"workload": ("BC1 IterativeClusterFit, 8192x8192 synthetic RGBA (noise_opaque, seed 3), PERCEPTUAL weights, sharded by block rows"
+                                    if iterative else
+                                    "BC1+BC3 ClusterFit, 8192x8192 synthetic RGBA (BC1: noise_opaque, BC3: noise_alpha, seed 3), "
+                                    "PERCEPTUAL weights, sharded by block rows"),
                        "blocks_per_format": (W // 4) * (H // 4), "parallelism": f"block-row shards x{world}, no collectives",
                        "l2": "256 MiB flush write before every timed kernel"},
             "per_format": {"bc1_mpix_s": W * H / (t1 / args.steps / 1e3) / 1e6, "bc3_mpix_s": (W * H / (t3 / args.steps / 1e3) / 1e6) if t3 else None,
