@@ -263,3 +263,28 @@ def test_batch_with_mips_matches_single_calls(T):
     if T.device_count() >= 2:
         outs2 = T.compress_batch_mips(2, texs, tp, n_gpus=2)
         assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))
+
+
+def test_concurrent_host_calls_are_thread_safe(T):
+    """The C ABI is documented as thread-safe: several host threads encoding different images at once (ctypes drops the
+    GIL) must each get the bytes a lone call produces."""
+    import threading
+    from texpresso_b200 import synth
+    jobs = [(fmt, alg, synth.generate("smooth" if k % 2 else "noise_alpha", 96 + 4 * k, 64 + 4 * k, seed=200 + k), 96 + 4 * k, 64 + 4 * k)
+            for k, (fmt, alg) in enumerate([(0, 1), (2, 1), (3, 1), (1, 0), (0, 2), (4, 1), (2, 2), (0, 0)])]
+    expect = [T.Format(f).compress(img, w, h, T.Params(T.Algorithm(a))) for f, a, img, w, h in jobs]
+    got = [None] * len(jobs)
+    errs = []
+
+    def work(i):
+        try:
+            f, a, img, w, h = jobs[i]
+            for _ in range(4):
+                got[i] = T.Format(f).compress(img, w, h, T.Params(T.Algorithm(a)))
+        except Exception as e:          # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errs, errs
+    assert all(np.array_equal(g, e) for g, e in zip(got, expect))

@@ -331,8 +331,10 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
             else if (format == BC2) colour_search_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
             else colour_search_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            TXP_CUDA(cudaGetLastError());
-            TXP_CUDA(cudaFreeAsync(setup, st));
+            const cudaError_t launch_err = cudaGetLastError();
+            const cudaError_t free_err = cudaFreeAsync(setup, st);      // stream-ordered: released after the search kernel
+            if (launch_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit launch: ") + cudaGetErrorString(launch_err));
+            TXP_CUDA(free_err);
         }
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
