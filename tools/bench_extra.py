@@ -27,7 +27,7 @@ def time_kernel(fn, reps, flush):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="bc4,bc5,range,iter,smooth,decode")
+    ap.add_argument("--cases", default="cfg2,bc4,bc5,range,iter,smooth,decode")
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
     torch.cuda.set_device(0); T.set_device(0)
@@ -90,6 +90,13 @@ def main():
                 ms, best = time_kernel(lambda: enc(fmt, img, w, h, T.Params(T.Algorithm.RangeFit, P, False), out), args.reps, flush)
                 report(f"{name}_rangefit_noise_opaque", w, h, ms, best, 64 + bs)
             del img
+    if "cfg2" in cases:
+        w = h = 4096                                      # BASELINE config 2: BC3 ClusterFit, 4096^2 noise_alpha, seed 2, default Params
+        img = torch.from_numpy(synth.generate("noise_alpha", w, h, 2).reshape(-1)).cuda()
+        out = torch.empty((w // 4) * (h // 4) * 16, dtype=torch.uint8, device="cuda")
+        ms, best = time_kernel(lambda: enc(T.Format.Bc3, img, w, h, T.Params(), out), args.reps, flush)
+        report("cfg2_bc3_cluster_noise_alpha", w, h, ms, best, 80, {"fp32_issue_frac": 967 * 159 * (w // 4) * (h // 4) / (ms / 1e3) / 37.22e12})
+        del img, out
     if "iter" in cases:
         w = h = 8192
         img = torch.from_numpy(synth.generate("noise_opaque", w, h, 3).reshape(-1)).cuda()
