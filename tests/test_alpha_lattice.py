@@ -1,0 +1,112 @@
+"""CPU check of the BC4/BC5 closed-form fast path (texpresso_b200/csrc/txp_alpha_lattice.cuh).
+
+The kernel's arithmetic for "regular" blocks (no 0 / 255, max - min >= 7) is restated in numpy from the generated
+table (texpresso_b200/csrc/alpha_lattice_data.h) and compared with the C oracle (alpha.rs:187-256) block by block:
+exhaustively over every range r = 7..255 and every offset inside the range, plus random regular blocks.  The GPU
+tests (test_gpu_parity / test_gpu_fuzz / test_gpu_alpha_lattice) then check the kernel itself."""
+import pathlib, re, struct, subprocess, sys
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+HDR = ROOT / "texpresso_b200" / "csrc" / "alpha_lattice_data.h"
+
+
+def load_table():
+    rows = re.findall(r"\{((?:0x[0-9A-F]{8}u(?:, )?){8})\}", HDR.read_text())
+    assert len(rows) == 256
+    tab = np.array([[int(x[:-1], 16) for x in r.split(", ")] for r in rows], dtype=np.uint32)
+    return tab
+
+
+def f32(bits):
+    return np.frombuffer(np.asarray(bits, dtype=np.uint32).tobytes(), dtype=np.float32).astype(np.float64)
+
+
+def emulate(values, tab):
+    """values: (n, 16) uint8 regular blocks -> (n, 8) uint8 BC4 blocks, step by step as the kernel does."""
+    v = values.astype(np.int64)
+    lo, hi = v.min(axis=1), v.max(axis=1)
+    r = hi - lo
+    assert (lo > 0).all() and (hi < 255).all() and (r >= 7).all()
+    row = tab[r]
+    a5, b5, a7, b7 = f32(row[:, 0]), f32(row[:, 1]), f32(row[:, 4]), f32(row[:, 5])
+    offs5 = np.stack([(row[:, 2 + k // 4] >> (8 * (k % 4))) & 255 for k in range(8)], axis=1).astype(np.int64)
+    offs7 = np.stack([(row[:, 6 + k // 4] >> (8 * (k % 4))) & 255 for k in range(8)], axis=1).astype(np.int64)
+    # d = vm - origin (exact), slot = low mantissa bits of fma(d, a, 1.5 * 2^23) = rint(d * a)
+    d5 = v - (lo[:, None] - b5[:, None])
+    s5 = np.rint(d5 * a5[:, None]).astype(np.int64)
+    d7 = v - (hi[:, None] + b7[:, None])
+    s7 = np.rint(d7 * -a7[:, None]).astype(np.int64)
+    assert s5.min() >= 0 and s5.max() <= 5 and s7.min() >= 0 and s7.max() <= 7
+    c5 = lo[:, None] + np.take_along_axis(offs5, s5, axis=1)
+    c7 = hi[:, None] - np.take_along_axis(offs7, s7, axis=1)
+    e5 = ((c5 - v) ** 2).sum(axis=1)
+    e7 = ((c7 - v) ** 2).sum(axis=1)
+    five = e5 <= e7
+    map5 = np.array([0, 2, 3, 4, 5, 1, 0, 0]); map7 = np.array([0, 2, 3, 4, 5, 6, 7, 1])
+    idx = np.where(five[:, None], map5[s5], map7[s7])
+    a0 = np.where(five, lo, hi); a1 = np.where(five, hi, lo)
+    bits = np.zeros(len(v), dtype=np.uint64)
+    for i in range(16):
+        bits |= idx[:, i].astype(np.uint64) << np.uint64(3 * i)
+    out = np.zeros((len(v), 8), dtype=np.uint8)
+    out[:, 0] = a0; out[:, 1] = a1
+    for k in range(6):
+        out[:, 2 + k] = ((bits >> np.uint64(8 * k)) & np.uint64(255)).astype(np.uint8)
+    return out
+
+
+def oracle_bc4(values):
+    n = len(values)
+    blocks = np.zeros((n, 16, 4), dtype=np.uint8)
+    blocks[:, :, 0] = values
+    blocks[:, :, 3] = 255
+    return O.compress_blocks(O.BC4, blocks, np.full(n, 0xFFFF, np.uint32))
+
+
+def test_table_is_current(tmp_path):
+    """the committed header is what tools/gen_alpha_lattice.py generates (its own exhaustive proof runs while generating)"""
+    before = HDR.read_text()
+    subprocess.run([sys.executable, str(ROOT / "tools" / "gen_alpha_lattice.py")], check=True, stdout=subprocess.DEVNULL)
+    assert HDR.read_text() == before
+
+
+def test_every_range_every_offset():
+    tab = load_table()
+    rng = np.random.default_rng(7)
+    blocks = []
+    for r in range(7, 254):
+        for lo in {1, 254 - r, int(rng.integers(1, 255 - r))}:
+            xs = np.arange(r + 1)
+            # 14 free pixels per block next to the two that pin lo and hi; cover every offset, in shuffled positions
+            for c in range(0, r + 1, 14):
+                fill = np.resize(xs[c:c + 14], 14)
+                vals = np.concatenate(([0, r], fill)) + lo
+                blocks.append(rng.permutation(vals))
+    values = np.array(blocks, dtype=np.uint8)
+    got = emulate(values, tab)
+    want = oracle_bc4(values)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (bad.size, values[bad[0]].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_regular_blocks(seed):
+    tab = load_table()
+    rng = np.random.default_rng(seed)
+    n = 60000
+    lo = rng.integers(1, 248, size=n)
+    hi = np.minimum(254, lo + rng.integers(7, 254, size=n))
+    values = (lo[:, None] + (rng.random((n, 16)) * (hi - lo + 1)[:, None]).astype(np.int64)).clip(1, 254)
+    # a third: values clustered near the lattice points / mid points (ties)
+    values[: n // 3] = (lo[: n // 3, None] + np.round(rng.integers(0, 15, size=(n // 3, 16)) * (hi - lo)[: n // 3, None] / 14.0)).clip(1, 254)
+    values = values.astype(np.uint8)
+    keep = (values.max(axis=1).astype(int) - values.min(axis=1)) >= 7
+    values = values[keep]
+    got = emulate(values, tab)
+    want = oracle_bc4(values)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (bad.size, values[bad[0]].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())

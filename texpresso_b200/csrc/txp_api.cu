@@ -17,6 +17,8 @@
 #include "single_lut_data.h"
 #include "txp_common.cuh"
 #include "txp_alpha.cuh"
+#include "alpha_lattice_data.h"
+#include "txp_alpha_lattice.cuh"
 #include "txp_colour.cuh"
 #include "txp_range.cuh"
 #include "txp_cluster_setup.cuh"
@@ -164,6 +166,7 @@ struct DeviceCtx {
     // release threshold: the default pool hands memory back to the OS at every synchronisation, which would put a
     // fresh device allocation inside every timed call.
     cudaMemPool_t pool = nullptr;
+    int sm_count = 0;
 };
 
 static DeviceCtx g_ctx[MAX_DEVICES];
@@ -196,6 +199,9 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         TXP_CUDA(cudaMemcpyToSymbol(g_tab3, t3.data(), TAB3_PAD * 4));
         TXP_CUDA(cudaMemcpyToSymbol(c_single_lut, lut, sizeof lut));
         TXP_CUDA(cudaMemcpyToSymbol(g_single_lut, lut, sizeof lut));
+        static_assert(sizeof(TXP_ALPHA_LATTICE) == 512 * sizeof(uint4), "alpha lattice table size");
+        TXP_CUDA(cudaMemcpyToSymbol(g_alpha_lattice, TXP_ALPHA_LATTICE, sizeof(TXP_ALPHA_LATTICE)));
+        TXP_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
@@ -283,9 +289,16 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
     if (src.nblocks > 0x7FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^31-1 blocks in one launch");
     const EncodeParams e = to_device_params(p);
     if (format == BC4 || format == BC5) {
-        // launch shape (threads per CTA, min CTAs per SM -> register cap); TXP_ALPHA_VARIANT is a tuning knob
-        static const int variant = [] { const char* e = getenv("TXP_ALPHA_VARIANT"); return e ? atoi(e) : -1; }();
+        // TXP_ALPHA_VARIANT (tuning knob): unset / 0 = lattice fast path + compacted literal path (txp_alpha_lattice.cuh);
+        // 1..5 = the literal one-thread-per-block kernel (txp_alpha.cuh) in different launch shapes, kept for A/B runs.
+        static const int variant = [] { const char* e = getenv("TXP_ALPHA_VARIANT"); return e ? atoi(e) : 0; }();
 #define TXP_ALPHA_LAUNCH(F, T, M) alpha_encode_kernel<F, T, M><<<(unsigned)((src.nblocks + (T) - 1) / (T)), T, 0, st>>>(src, d_out)
+#define TXP_LATTICE_LAUNCH(F, T, M)                                                                                   \
+    do {                                                                                                              \
+        const uint32_t ntiles = (uint32_t)((src.nblocks + 31) / 32);                                                  \
+        const uint32_t need = (ntiles + (T) / 32 - 1) / ((T) / 32), cap = (uint32_t)ctx.sm_count * (M);               \
+        alpha_lattice_kernel<F, T, M><<<need < cap ? need : cap, T, 0, st>>>(src, d_out, ntiles);                     \
+    } while (0)
         if (format == BC4) {
             switch (variant) {
             case 1: TXP_ALPHA_LAUNCH(BC4, 128, 8); break;
@@ -293,7 +306,10 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
             case 3: TXP_ALPHA_LAUNCH(BC4, 256, 3); break;
             case 4: TXP_ALPHA_LAUNCH(BC4, 64, 16); break;
             case 5: TXP_ALPHA_LAUNCH(BC4, 256, 4); break;
-            default: TXP_ALPHA_LAUNCH(BC4, 128, 8); break;   // 64 registers, 32 warps/SM: best of the sweep (profiles/README.md)
+            case 6: TXP_LATTICE_LAUNCH(BC4, 128, 6); break;
+            case 7: TXP_LATTICE_LAUNCH(BC4, 256, 4); break;
+            case 8: TXP_LATTICE_LAUNCH(BC4, 256, 2); break;
+            default: TXP_LATTICE_LAUNCH(BC4, 256, 3); break;
             }
         } else {
             switch (variant) {
@@ -302,9 +318,13 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
             case 3: TXP_ALPHA_LAUNCH(BC5, 256, 3); break;
             case 4: TXP_ALPHA_LAUNCH(BC5, 64, 16); break;
             case 5: TXP_ALPHA_LAUNCH(BC5, 256, 4); break;
-            default: TXP_ALPHA_LAUNCH(BC5, 128, 6); break;   // 80 registers, 24 warps/SM
+            case 6: TXP_LATTICE_LAUNCH(BC5, 128, 6); break;
+            case 7: TXP_LATTICE_LAUNCH(BC5, 256, 4); break;
+            case 8: TXP_LATTICE_LAUNCH(BC5, 256, 2); break;
+            default: TXP_LATTICE_LAUNCH(BC5, 256, 3); break;
             }
         }
+#undef TXP_LATTICE_LAUNCH
 #undef TXP_ALPHA_LAUNCH
     } else if (e.algorithm == RANGE_FIT) {
         // RangeFit: one thread per block (txp_range.cuh)
