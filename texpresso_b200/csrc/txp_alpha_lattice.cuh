@@ -178,4 +178,111 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_kernel(const 
     if (lane < qn) alpha_drain_item<FMT>(src, out, q[lane]);
 }
 
+
+// ---- image-mode kernel: same algorithm, block rows staged through shared memory with cp.async ----------------------
+// For a plain w x h image with 16-byte aligned rows (BlockSource::vec_ok, one level) each lane prefetches the four
+// 16-byte row segments of its block STAGES-1 tiles ahead into its own 64 bytes of a per-warp ring buffer
+// (LDGSTS, no registers held across the wait), and block coordinates advance incrementally (step_q/step_r =
+// quotient / remainder of the per-iteration block stride by the blocks-per-row count, computed by the host)
+// instead of a division per block.  A lane only ever reads the bytes it copied itself, so cp.async.wait_group
+// is the only synchronisation.  Partial bottom rows (h % 4 != 0) go to the literal path through the queue.
+__device__ __forceinline__ void cp_async16(const uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int THREADS, int STAGES>
+constexpr size_t lattice_image_smem() { return 512 * sizeof(uint4) + (size_t)THREADS * STAGES * 64 + (THREADS / 32) * LATTICE_QUEUE * sizeof(uint32_t); }
+
+template <int FMT, int THREADS, int MIN_CTAS, int STAGES>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(const __grid_constant__ BlockSource src, uint8_t* __restrict__ out,
+                                                                               const uint32_t ntiles, const uint32_t step_q, const uint32_t step_r) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* tab = reinterpret_cast<uint4*>(smem_raw);
+    uint4* ring = tab + 512;                                                          // [warp][stage][row][lane]
+    uint32_t* queue = reinterpret_cast<uint32_t*>(ring + THREADS * STAGES * 4);
+    for (int i = threadIdx.x; i < 512; i += THREADS) tab[i] = g_alpha_lattice[i];
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t* q = queue + warp * LATTICE_QUEUE;
+    uint32_t qn = 0;
+    const uint32_t stride = gridDim.x * (THREADS / 32);
+    const uint32_t bw = src.bw, nblocks = (uint32_t)src.nblocks, full_rows = src.h >> 2;   // block rows with 4 pixel rows
+    const size_t pitch = (size_t)src.w * 4;
+    uint4* my = ring + (warp * STAGES * 4) * 32 + lane;                               // + (stage * 4 + row) * 32
+    const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
+
+    const uint32_t tile0 = blockIdx.x * (THREADS / 32) + warp;
+    // prefetch stream
+    uint32_t pb = tile0 * 32 + lane, pby = pb / bw, pbx = pb - pby * bw, pst = 0;
+    auto prefetch = [&]() {
+        if (pb < nblocks && pby < full_rows) {
+            const uint8_t* g = src.rgba + (size_t)pby * 4 * pitch + (size_t)pbx * 16;
+            const uint32_t s = my_s + pst * (4 * 32 * 16);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) cp_async16(s + r * (32 * 16), g + r * pitch);
+        }
+        cp_async_commit();
+        pb += stride * 32; pbx += step_r; pby += step_q;
+        if (pbx >= bw) { pbx -= bw; ++pby; }
+        pst = pst + 1 == STAGES ? 0 : pst + 1;
+    };
+#pragma unroll
+    for (int i = 0; i < STAGES - 1; ++i) prefetch();
+
+    uint32_t b = tile0 * 32 + lane, by = b / bw, bx = b - by * bw, st = 0;
+#pragma unroll 1
+    for (uint32_t tile = tile0; tile < ntiles; tile += stride) {
+        prefetch();
+        cp_async_wait<STAGES - 1>();
+        bool todo0 = false, todo1 = false;
+        if (b < nblocks) {
+            if (by < full_rows) {
+                uint32_t px[16];
+                const uint4* sp = my + st * (4 * 32);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { const uint4 v = sp[r * 32]; px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w; }
+                uint2 r0, r1;
+                const bool ok0 = alpha_fit_lattice<0>(px, tab, r0);
+                todo0 = !ok0;
+                if (FMT == BC4) {
+                    if (ok0) reinterpret_cast<uint2*>(out)[b] = r0;
+                } else {
+                    const bool ok1 = alpha_fit_lattice<1>(px, tab, r1);
+                    todo1 = !ok1;
+                    if (ok0 && ok1) reinterpret_cast<uint4*>(out)[b] = make_uint4(r0.x, r0.y, r1.x, r1.y);
+                    else if (ok0) reinterpret_cast<uint2*>(out)[2 * (size_t)b] = r0;
+                    else if (ok1) reinterpret_cast<uint2*>(out)[2 * (size_t)b + 1] = r1;
+                }
+            } else {
+                todo0 = true; todo1 = FMT == BC5;
+            }
+        }
+        const uint32_t m0 = __ballot_sync(FULL, todo0);
+        if (todo0) q[qn + __popc(m0 & lt)] = b;
+        qn += __popc(m0);
+        if (FMT == BC5) {
+            const uint32_t m1 = __ballot_sync(FULL, todo1);
+            if (todo1) q[qn + __popc(m1 & lt)] = b | 0x80000000u;
+            qn += __popc(m1);
+        }
+        __syncwarp();
+#pragma unroll 1
+        while (qn >= 32) {
+            qn -= 32;
+            const uint32_t item = q[qn + lane];
+            __syncwarp();
+            alpha_drain_item<FMT>(src, out, item);
+        }
+        b += stride * 32; bx += step_r; by += step_q;
+        if (bx >= bw) { bx -= bw; ++by; }
+        st = st + 1 == STAGES ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
+    if (lane < qn) alpha_drain_item<FMT>(src, out, q[lane]);
+}
+
 }  // namespace txp

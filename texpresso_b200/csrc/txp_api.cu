@@ -26,6 +26,11 @@
 
 namespace txp {
 
+#ifndef TXP_LATTICE_STAGES
+#define TXP_LATTICE_STAGES 3
+#endif
+constexpr int LATTICE_STAGES = TXP_LATTICE_STAGES;   // cp.async ring depth of alpha_lattice_image_kernel
+
 // ---------------------------------------------------------------------------------------------------
 // BC1/BC2/BC3 encoder kernel: one warp per block (see txp_colour.cuh)
 // ---------------------------------------------------------------------------------------------------
@@ -202,6 +207,10 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         static_assert(sizeof(TXP_ALPHA_LATTICE) == 512 * sizeof(uint4), "alpha lattice table size");
         TXP_CUDA(cudaMemcpyToSymbol(g_alpha_lattice, TXP_ALPHA_LATTICE, sizeof(TXP_ALPHA_LATTICE)));
         TXP_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
+#define TXP_LATTICE_ATTR(F, T, M) TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_image_smem<T, LATTICE_STAGES>()))
+        TXP_LATTICE_ATTR(BC4, 128, 6); TXP_LATTICE_ATTR(BC4, 256, 4); TXP_LATTICE_ATTR(BC4, 256, 2); TXP_LATTICE_ATTR(BC4, 256, 3);
+        TXP_LATTICE_ATTR(BC5, 128, 6); TXP_LATTICE_ATTR(BC5, 256, 4); TXP_LATTICE_ATTR(BC5, 256, 2); TXP_LATTICE_ATTR(BC5, 256, 3);
+#undef TXP_LATTICE_ATTR
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
@@ -297,8 +306,17 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
     do {                                                                                                              \
         const uint32_t ntiles = (uint32_t)((src.nblocks + 31) / 32);                                                  \
         const uint32_t need = (ntiles + (T) / 32 - 1) / ((T) / 32), cap = (uint32_t)ctx.sm_count * (M);               \
-        alpha_lattice_kernel<F, T, M><<<need < cap ? need : cap, T, 0, st>>>(src, d_out, ntiles);                     \
+        const uint32_t grid = need < cap ? need : cap;                                                                \
+        if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged) {                                           \
+            /* plain aligned image: cp.async-staged kernel; per-iteration block stride as (quotient, remainder) of bw */ \
+            const uint64_t step = (uint64_t)grid * ((T) / 32) * 32;                                                   \
+            alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES><<<grid, T, lattice_image_smem<T, LATTICE_STAGES>(), st>>>(             \
+                src, d_out, ntiles, (uint32_t)(step / src.bw), (uint32_t)(step % src.bw));                            \
+        } else {                                                                                                      \
+            alpha_lattice_kernel<F, T, M><<<grid, T, 0, st>>>(src, d_out, ntiles);                                    \
+        }                                                                                                             \
     } while (0)
+        static const bool alpha_staged = [] { const char* e = getenv("TXP_ALPHA_STAGED"); return !e || atoi(e) != 0; }();
         if (format == BC4) {
             switch (variant) {
             case 1: TXP_ALPHA_LAUNCH(BC4, 128, 8); break;
