@@ -32,6 +32,20 @@ namespace txp {
 
 __device__ uint4 g_alpha_lattice[512];            // TXP_ALPHA_LATTICE (alpha_lattice_data.h), copied at context creation
 
+// tuning knobs (tools/micro/alpha_ab.cu measures them; defaults = best measured)
+#ifndef TXP_LAT_ERR
+#define TXP_LAT_ERR 0      // 1: sum c^2 - 2 sum c v with two IDP.4A;  0: VABSDIFF4 + IDP.4A
+#endif
+#ifndef TXP_LAT_VMG
+#define TXP_LAT_VMG 0      // G channel -> fp32 mantissa: 0 = PRMT, 1 = LOP3 (two of them: LOP3 takes one immediate), 2 = LOP3 with the magic in a register
+#endif
+#ifndef TXP_LAT_VMR
+#define TXP_LAT_VMR 0      // R channel -> fp32 mantissa: 0 = PRMT, 1 = SHF + LOP3, 2 = LOP3 + IMAD
+#endif
+#ifndef TXP_LAT_MM
+#define TXP_LAT_MM 0       // min / max: 0 = VIMNMX3 trees, 1 = two-input VIMNMX
+#endif
+
 constexpr uint32_t MAGIC15 = 0x47400000u;         // 1.5 * 2^15 as fp32 bits
 constexpr float MAGIC23 = 12582912.0f;            // 1.5 * 2^23
 
@@ -43,11 +57,14 @@ __device__ __forceinline__ uint32_t prmt(const uint32_t a, const uint32_t b, con
 
 // One book over 16 pixels.  vm: the pixels as 1.5*2^15 + v; V: the same values as packed bytes (4 per word);
 // origin / a: d = vm - origin, slot = rint(d * a) (a < 0 for the 7-point book: x = hi - v);
-// clo/chi: the codes of slots 0..7 as bytes.  Returns sum (v - code)^2; sel[k] holds the slots of pixels 4k..4k+3 as nibbles.
-__device__ __forceinline__ uint32_t lattice_book(const uint32_t vm[16], const uint32_t V[4], const float origin, const float a,
-                                                 const uint32_t clo, const uint32_t chi, uint32_t sel[4]) {
+// clo/chi: the codes of slots 0..7 as bytes.  sel[k] holds the slots of pixels 4k..4k+3 as nibbles.
+// Returns sum(c^2) - 2 sum(c v) = sum (v - c)^2 - sum v^2 over the chosen codes c: the sum v^2 is the same for both
+// books, so err5 <= err7 (alpha.rs:251) is decided on these values.  (Two IDP.4A on the FMA pipe instead of
+// VABSDIFF4 + IDP.4A: the ALU pipe, where PRMT / VIMNMX3 / VABSDIFF4 all run at half rate, is the busier one.)
+__device__ __forceinline__ int lattice_book(const uint32_t vm[16], const uint32_t V[4], const float origin, const float a,
+                                            const uint32_t clo, const uint32_t chi, uint32_t sel[4]) {
     const f32x2 o2 = pk(origin, origin), a2 = pk(a, a), m2 = pk(MAGIC23, MAGIC23);
-    uint32_t err = 0;
+    uint32_t cc = 0, cv = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const f32x2 d01 = sub2(pk(__uint_as_float(vm[4 * k]), __uint_as_float(vm[4 * k + 1])), o2);
@@ -59,41 +76,43 @@ __device__ __forceinline__ uint32_t lattice_book(const uint32_t vm[16], const ui
         const uint32_t s = ((__float_as_uint(t3) * 16u + __float_as_uint(t2)) * 16u + __float_as_uint(t1)) * 16u + __float_as_uint(t0);
         sel[k] = s;
         const uint32_t c4 = prmt(clo, chi, s);
+#if TXP_LAT_ERR
+        cc = __dp4a(c4, c4, cc);
+        cv = __dp4a(c4, V[k], cv);
+#else
         const uint32_t e4 = __vabsdiffu4(c4, V[k]);
-        err = __dp4a(e4, e4, err);
+        cc = __dp4a(e4, e4, cc);
+#endif
     }
-    return err;
+    return (int)cc - 2 * (int)cv;
 }
 
-// One channel (byte CH of every RGBA word) of one fully valid block.  Returns false if the block is not regular.
-template <int CH>
-__device__ __forceinline__ bool alpha_fit_lattice(const uint32_t px[16], const uint4* __restrict__ tab, uint2& out) {
-    uint32_t vm[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) vm[i] = prmt(MAGIC15, px[i], CH == 0 ? 0x3240u : 0x3250u);   // (0x00, v, 0x40, 0x47)
+// One channel of one fully valid block, given as vm[i] = 1.5*2^15 + v_i (fp32 bits) and V = the same 16 values as
+// packed bytes.  Returns false if the block is not regular.
+__device__ __forceinline__ bool alpha_fit_lattice(const uint32_t vm[16], const uint32_t V[4], const uint4* __restrict__ tab, uint2& out) {
     // min / max on the raw bits (positive floats order like integers)
+#if TXP_LAT_MM
+    uint32_t mn = min(vm[0], vm[1]), mx = max(vm[0], vm[1]);
+#pragma unroll
+    for (int i = 2; i < 16; ++i) { mn = min(mn, vm[i]); mx = max(mx, vm[i]); }
+#else
     uint32_t mn = __vimin3_u32(vm[0], vm[1], vm[2]), mx = __vimax3_u32(vm[0], vm[1], vm[2]);
 #pragma unroll
     for (int i = 3; i < 15; i += 2) { mn = __vimin3_u32(mn, vm[i], vm[i + 1]); mx = __vimax3_u32(mx, vm[i], vm[i + 1]); }
     mn = min(mn, vm[15]); mx = max(mx, vm[15]);
+#endif
     const uint32_t span = mx - mn;                                     // r << 8
     if (!(mn > MAGIC15 && mx < (MAGIC15 | 0xFF00u) && span >= (7u << 8))) return false;
 
     const uint4 e5 = tab[span >> 7], e7 = tab[(span >> 7) + 1];        // row r = two uint4
     const uint32_t lo = (mn >> 8) & 255u, hi = (mx >> 8) & 255u;
-    uint32_t V[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t s2 = CH == 0 ? 0x0040u : 0x0051u;               // byte CH of both words
-        V[k] = __byte_perm(__byte_perm(px[4 * k], px[4 * k + 1], s2), __byte_perm(px[4 * k + 2], px[4 * k + 3], s2), 0x5410u);
-    }
     uint32_t s5[4], s7[4];
     // 5-point book from lo: x = v - lo, origin = lo - beta5, codes lo + offs
-    const uint32_t err5 = lattice_book(vm, V, __fsub_rn(__uint_as_float(mn), __uint_as_float(e5.y)), __uint_as_float(e5.x),
-                                       e5.z + lo * 0x01010101u, e5.w + lo * 0x01010101u, s5);
+    const int err5 = lattice_book(vm, V, __fsub_rn(__uint_as_float(mn), __uint_as_float(e5.y)), __uint_as_float(e5.x),
+                                  e5.z + lo * 0x01010101u, e5.w + lo * 0x01010101u, s5);
     // 7-point book from hi: x = hi - v = -(v - (hi + beta7)), codes hi - offs
-    const uint32_t err7 = lattice_book(vm, V, __fadd_rn(__uint_as_float(mx), __uint_as_float(e7.y)), -__uint_as_float(e7.x),
-                                       hi * 0x01010101u - e7.z, hi * 0x01010101u - e7.w, s7);
+    const int err7 = lattice_book(vm, V, __fadd_rn(__uint_as_float(mx), __uint_as_float(e7.y)), -__uint_as_float(e7.x),
+                                  hi * 0x01010101u - e7.z, hi * 0x01010101u - e7.w, s7);
     const bool five = err5 <= err7;                                    // alpha.rs:251
     const uint32_t a0 = five ? lo : hi, a1 = five ? hi : lo;          // write_alpha_block5 as is / write_alpha_block7 swapped
     const uint32_t mhi = five ? 0x00000105u : 0x01070605u;            // slot -> index: 0 -> 0, N -> 1, s -> s + 1
@@ -109,75 +128,149 @@ __device__ __forceinline__ bool alpha_fit_lattice(const uint32_t px[16], const u
     return true;
 }
 
-// literal path for one queued (block, channel) item
+// Both channel fits of one fully valid block.  R (byte 0) and G (byte 1) are lifted into the fp32 mantissa with one
+// PRMT each; the packed-byte forms of both channels (VR, VG: also what an irregular channel is queued as) share
+// their first PRMT level.
 template <int FMT>
-__device__ __noinline__ void alpha_drain_item(const BlockSource& src, uint8_t* __restrict__ out, const uint32_t item) {
-    const uint32_t b = item & 0x7FFFFFFFu, ch = item >> 31;
-    uint32_t px[16], mask;
-    load_block_thread(src, b, px, mask);
-    uint32_t v[16];
+__device__ __forceinline__ void alpha_fit_block(const uint32_t px[16], const uint4* __restrict__ tab, bool& ok0, uint2& r0, uint32_t VR[4],
+                                                bool& ok1, uint2& r1, uint32_t VG[4]) {
+    uint32_t vm[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = (px[i] >> (8 * ch)) & 255u;    // lib.rs:200, :202-203
-    const uint2 r = mask == 0xFFFFu ? alpha_fit_full(v) : alpha_fit_thread(v, mask);
+    for (int k = 0; k < 4; ++k) {
+        if (FMT == BC4) {
+            VR[k] = prmt(prmt(px[4 * k], px[4 * k + 1], 0x0040u), prmt(px[4 * k + 2], px[4 * k + 3], 0x0040u), 0x5410u);
+        } else {
+            const uint32_t t0 = prmt(px[4 * k], px[4 * k + 1], 0x5140u), t1 = prmt(px[4 * k + 2], px[4 * k + 3], 0x5140u);   // (R, R', G, G')
+            VR[k] = prmt(t0, t1, 0x5410u);
+            VG[k] = prmt(t0, t1, 0x7632u);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+#if TXP_LAT_VMR == 0
+        vm[i] = prmt(MAGIC15, px[i], 0x3240u);                                       // bytes (0x00, R, 0x40, 0x47)
+#elif TXP_LAT_VMR == 1
+        vm[i] = ((px[i] << 8) & 0xFF00u) | MAGIC15;
+#else
+        vm[i] = (px[i] & 0xFFu) * 256u + MAGIC15;
+#endif
+    }
+    ok0 = alpha_fit_lattice(vm, VR, tab, r0);
+    ok1 = true;
+    if (FMT == BC5) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+#if TXP_LAT_VMG == 0
+            vm[i] = prmt(MAGIC15, px[i], 0x3250u);
+#elif TXP_LAT_VMG == 1
+            vm[i] = (px[i] & 0xFF00u) | MAGIC15;
+#else
+            uint32_t magic; asm volatile("mov.u32 %0, 0x47400000;" : "=r"(magic));
+            vm[i] = (px[i] & 0xFF00u) | magic;
+#endif
+        }
+        ok1 = alpha_fit_lattice(vm, VG, tab, r1);
+    }
+}
+
+// ---- per-warp queue of irregular (block, channel) items ------------------------------------------------------------
+// meta = block | RELOAD << 30 | channel << 31.  Fully valid blocks carry their 16 channel values as packed bytes, so
+// the literal path needs no second trip to memory; partial (edge) blocks are re-gathered with their mask (RELOAD).
+constexpr int LATTICE_QUEUE = 96;                 // <= 31 left over + 2 x 32 new items per tile
+constexpr uint32_t ITEM_RELOAD = 0x40000000u, ITEM_BLOCK = 0x3FFFFFFFu;
+struct WarpQueue {
+    uint4 vals[LATTICE_QUEUE];
+    uint32_t meta[LATTICE_QUEUE];
+};
+
+template <int FMT>
+__device__ __noinline__ void alpha_drain_item(const BlockSource& src, uint8_t* __restrict__ out, const uint32_t meta, const uint4 V) {
+#ifdef TXP_LAT_NODRAIN            // measurement only (tools/micro/alpha_ab.cu): cost of the literal path
+    return;
+#endif
+    const uint32_t b = meta & ITEM_BLOCK, ch = meta >> 31;
+    uint32_t v[16];
+    uint2 r;
+    if (meta & ITEM_RELOAD) {
+        uint32_t px[16], mask;
+        load_block_thread(src, b, px, mask);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (px[i] >> (8 * ch)) & 255u;    // lib.rs:200, :202-203
+        r = alpha_fit_thread(v, mask);
+    } else {
+        const uint32_t w[4] = {V.x, V.y, V.z, V.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+        r = alpha_fit_full(v);
+    }
     reinterpret_cast<uint2*>(out)[FMT == BC4 ? (size_t)b : 2 * (size_t)b + ch] = r;
 }
 
-constexpr int LATTICE_QUEUE = 96;                 // <= 31 left over + 2 x 32 new items per tile
+// push this tile's irregular items (ballot-compacted), then run the literal path on full warps of queued items
+template <int FMT>
+__device__ __forceinline__ void queue_push_drain(WarpQueue& q, uint32_t& qn, const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out,
+                                                 const uint32_t b, const bool todo0, const uint32_t reload0, const uint32_t V0[4],
+                                                 const bool todo1, const uint32_t V1[4]) {
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t m0 = __ballot_sync(FULL, todo0);
+    if (todo0) { const uint32_t i = qn + __popc(m0 & lt); q.meta[i] = b | reload0; q.vals[i] = make_uint4(V0[0], V0[1], V0[2], V0[3]); }
+    qn += __popc(m0);
+    if (FMT == BC5) {
+        const uint32_t m1 = __ballot_sync(FULL, todo1);
+        if (todo1) { const uint32_t i = qn + __popc(m1 & lt); q.meta[i] = b | reload0 | 0x80000000u; q.vals[i] = make_uint4(V1[0], V1[1], V1[2], V1[3]); }
+        qn += __popc(m1);
+    }
+    __syncwarp();
+#pragma unroll 1
+    while (qn >= 32) {
+        qn -= 32;
+        const uint32_t meta = q.meta[qn + lane];
+        const uint4 V = q.vals[qn + lane];
+        __syncwarp();
+        alpha_drain_item<FMT>(src, out, meta, V);
+    }
+}
 
+template <int FMT>
+__device__ __forceinline__ void queue_flush(WarpQueue& q, const uint32_t qn, const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out) {
+    if (lane < qn) alpha_drain_item<FMT>(src, out, q.meta[lane], q.vals[lane]);
+}
+
+// ---- general kernel: list mode, mip chains, unaligned widths (direct loads) -----------------------------------------
 template <int FMT, int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_kernel(const __grid_constant__ BlockSource src, uint8_t* __restrict__ out, const uint32_t ntiles) {
     __shared__ uint4 tab[512];
-    __shared__ uint32_t queue[THREADS / 32][LATTICE_QUEUE];
+    __shared__ WarpQueue queues[THREADS / 32];
     for (int i = threadIdx.x; i < 512; i += THREADS) tab[i] = g_alpha_lattice[i];
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t* q = queue[warp];
+    WarpQueue& q = queues[warp];
     uint32_t qn = 0;
     const uint32_t stride = gridDim.x * (THREADS / 32);
+#pragma unroll 1
     for (uint32_t tile = blockIdx.x * (THREADS / 32) + warp; tile < ntiles; tile += stride) {
-        const uint64_t b = (uint64_t)tile * 32 + lane;
+        const uint32_t b = tile * 32 + lane;
         bool todo0 = false, todo1 = false;
+        uint32_t reload = 0, VR[4] = {0, 0, 0, 0}, VG[4] = {0, 0, 0, 0};
         if (b < src.nblocks) {
             uint32_t px[16], mask;
             load_block_thread(src, b, px, mask);
             if (mask == 0xFFFFu) {
                 uint2 r0, r1;
-                const bool ok0 = alpha_fit_lattice<0>(px, tab, r0);
-                todo0 = !ok0;
-                if (FMT == BC4) {
-                    if (ok0) reinterpret_cast<uint2*>(out)[b] = r0;
-                } else {
-                    const bool ok1 = alpha_fit_lattice<1>(px, tab, r1);
-                    todo1 = !ok1;
-                    if (ok0 && ok1) reinterpret_cast<uint4*>(out)[b] = make_uint4(r0.x, r0.y, r1.x, r1.y);
-                    else if (ok0) reinterpret_cast<uint2*>(out)[2 * b] = r0;
-                    else if (ok1) reinterpret_cast<uint2*>(out)[2 * b + 1] = r1;
-                }
+                bool ok0, ok1;
+                alpha_fit_block<FMT>(px, tab, ok0, r0, VR, ok1, r1, VG);
+                todo0 = !ok0; todo1 = !ok1;
+                uint2* o2 = reinterpret_cast<uint2*>(out) + (FMT == BC4 ? (size_t)b : 2 * (size_t)b);
+                if (ok0) o2[0] = r0;
+                if (FMT == BC5 && ok1) o2[1] = r1;
             } else {
-                todo0 = true; todo1 = FMT == BC5;
+                todo0 = true; todo1 = FMT == BC5; reload = ITEM_RELOAD;
             }
         }
-        const uint32_t m0 = __ballot_sync(FULL, todo0);
-        if (todo0) q[qn + __popc(m0 & lt)] = (uint32_t)b;
-        qn += __popc(m0);
-        if (FMT == BC5) {
-            const uint32_t m1 = __ballot_sync(FULL, todo1);
-            if (todo1) q[qn + __popc(m1 & lt)] = (uint32_t)b | 0x80000000u;
-            qn += __popc(m1);
-        }
-        __syncwarp();
-#pragma unroll 1
-        while (qn >= 32) {
-            qn -= 32;
-            const uint32_t item = q[qn + lane];
-            __syncwarp();
-            alpha_drain_item<FMT>(src, out, item);
-        }
+        queue_push_drain<FMT>(q, qn, lane, src, out, b, todo0, reload, VR, todo1, VG);
     }
-    if (lane < qn) alpha_drain_item<FMT>(src, out, q[lane]);
+    queue_flush<FMT>(q, qn, lane, src, out);
 }
-
 
 // ---- image-mode kernel: same algorithm, block rows staged through shared memory with cp.async ----------------------
 // For a plain w x h image with 16-byte aligned rows (BlockSource::vec_ok, one level) each lane prefetches the four
@@ -194,7 +287,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int THREADS, int STAGES>
-constexpr size_t lattice_image_smem() { return 512 * sizeof(uint4) + (size_t)THREADS * STAGES * 64 + (THREADS / 32) * LATTICE_QUEUE * sizeof(uint32_t); }
+constexpr size_t lattice_image_smem() { return 512 * sizeof(uint4) + (size_t)THREADS * STAGES * 64 + (THREADS / 32) * sizeof(WarpQueue); }
 
 template <int FMT, int THREADS, int MIN_CTAS, int STAGES>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(const __grid_constant__ BlockSource src, uint8_t* __restrict__ out,
@@ -202,87 +295,69 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* tab = reinterpret_cast<uint4*>(smem_raw);
     uint4* ring = tab + 512;                                                          // [warp][stage][row][lane]
-    uint32_t* queue = reinterpret_cast<uint32_t*>(ring + THREADS * STAGES * 4);
+    WarpQueue* queues = reinterpret_cast<WarpQueue*>(ring + THREADS * STAGES * 4);
     for (int i = threadIdx.x; i < 512; i += THREADS) tab[i] = g_alpha_lattice[i];
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t* q = queue + warp * LATTICE_QUEUE;
+    WarpQueue& q = queues[warp];
     uint32_t qn = 0;
     const uint32_t stride = gridDim.x * (THREADS / 32);
     const uint32_t bw = src.bw, nblocks = (uint32_t)src.nblocks, full_rows = src.h >> 2;   // block rows with 4 pixel rows
-    const size_t pitch = (size_t)src.w * 4;
+    const uint32_t pitch = src.w * 4;                                                 // image bytes < 2^32 (checked by the host)
     uint4* my = ring + (warp * STAGES * 4) * 32 + lane;                               // + (stage * 4 + row) * 32
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
+    const uint32_t stride32 = stride * 32;
+    const uint32_t step_off = step_q * 4 * pitch + step_r * 16, wrap_off = 4 * pitch - bw * 16;
 
+    // prefetch stream: block index, block coordinates and byte offset of the block STAGES-1 tiles ahead
     const uint32_t tile0 = blockIdx.x * (THREADS / 32) + warp;
-    // prefetch stream
-    uint32_t pb = tile0 * 32 + lane, pby = pb / bw, pbx = pb - pby * bw, pst = 0;
+    uint32_t pb = tile0 * 32 + lane, pby = pb / bw, pbx = pb - pby * bw, poff = pby * 4 * pitch + pbx * 16, pst = 0;
+    uint32_t staged = 0;                                                              // bit k: the tile issued k prefetches ago was staged
     auto prefetch = [&]() {
-        if (pb < nblocks && pby < full_rows) {
-            const uint8_t* g = src.rgba + (size_t)pby * 4 * pitch + (size_t)pbx * 16;
+        const bool ok = pb < nblocks && pby < full_rows;
+        if (ok) {
+            const uint8_t* g = src.rgba + poff;
             const uint32_t s = my_s + pst * (4 * 32 * 16);
 #pragma unroll
             for (int r = 0; r < 4; ++r) cp_async16(s + r * (32 * 16), g + r * pitch);
         }
         cp_async_commit();
-        pb += stride * 32; pbx += step_r; pby += step_q;
-        if (pbx >= bw) { pbx -= bw; ++pby; }
+        staged = (staged << 1) | (ok ? 1u : 0u);
+        pb += stride32; pbx += step_r; pby += step_q; poff += step_off;
+        if (pbx >= bw) { pbx -= bw; ++pby; poff += wrap_off; }
         pst = pst + 1 == STAGES ? 0 : pst + 1;
     };
 #pragma unroll
     for (int i = 0; i < STAGES - 1; ++i) prefetch();
 
-    uint32_t b = tile0 * 32 + lane, by = b / bw, bx = b - by * bw, st = 0;
+    uint32_t st = 0;
 #pragma unroll 1
     for (uint32_t tile = tile0; tile < ntiles; tile += stride) {
         prefetch();
         cp_async_wait<STAGES - 1>();
+        const uint32_t b = pb - STAGES * stride32;                                    // this tile's block of this lane
         bool todo0 = false, todo1 = false;
-        if (b < nblocks) {
-            if (by < full_rows) {
-                uint32_t px[16];
-                const uint4* sp = my + st * (4 * 32);
+        uint32_t reload = 0, VR[4] = {0, 0, 0, 0}, VG[4] = {0, 0, 0, 0};
+        if ((staged >> (STAGES - 1)) & 1u) {
+            uint32_t px[16];
+            const uint4* sp = my + st * (4 * 32);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) { const uint4 v = sp[r * 32]; px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w; }
-                uint2 r0, r1;
-                const bool ok0 = alpha_fit_lattice<0>(px, tab, r0);
-                todo0 = !ok0;
-                if (FMT == BC4) {
-                    if (ok0) reinterpret_cast<uint2*>(out)[b] = r0;
-                } else {
-                    const bool ok1 = alpha_fit_lattice<1>(px, tab, r1);
-                    todo1 = !ok1;
-                    if (ok0 && ok1) reinterpret_cast<uint4*>(out)[b] = make_uint4(r0.x, r0.y, r1.x, r1.y);
-                    else if (ok0) reinterpret_cast<uint2*>(out)[2 * (size_t)b] = r0;
-                    else if (ok1) reinterpret_cast<uint2*>(out)[2 * (size_t)b + 1] = r1;
-                }
-            } else {
-                todo0 = true; todo1 = FMT == BC5;
-            }
+            for (int r = 0; r < 4; ++r) { const uint4 v = sp[r * 32]; px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w; }
+            uint2 r0, r1;
+            bool ok0, ok1;
+            alpha_fit_block<FMT>(px, tab, ok0, r0, VR, ok1, r1, VG);
+            todo0 = !ok0; todo1 = !ok1;
+            uint2* o2 = reinterpret_cast<uint2*>(out) + (FMT == BC4 ? (size_t)b : 2 * (size_t)b);
+            if (ok0) o2[0] = r0;
+            if (FMT == BC5 && ok1) o2[1] = r1;
+        } else if (b < nblocks) {                                                     // partial bottom row
+            todo0 = true; todo1 = FMT == BC5; reload = ITEM_RELOAD;
         }
-        const uint32_t m0 = __ballot_sync(FULL, todo0);
-        if (todo0) q[qn + __popc(m0 & lt)] = b;
-        qn += __popc(m0);
-        if (FMT == BC5) {
-            const uint32_t m1 = __ballot_sync(FULL, todo1);
-            if (todo1) q[qn + __popc(m1 & lt)] = b | 0x80000000u;
-            qn += __popc(m1);
-        }
-        __syncwarp();
-#pragma unroll 1
-        while (qn >= 32) {
-            qn -= 32;
-            const uint32_t item = q[qn + lane];
-            __syncwarp();
-            alpha_drain_item<FMT>(src, out, item);
-        }
-        b += stride * 32; bx += step_r; by += step_q;
-        if (bx >= bw) { bx -= bw; ++by; }
+        queue_push_drain<FMT>(q, qn, lane, src, out, b, todo0, reload, VR, todo1, VG);
         st = st + 1 == STAGES ? 0 : st + 1;
     }
     cp_async_wait<0>();
-    if (lane < qn) alpha_drain_item<FMT>(src, out, q[lane]);
+    queue_flush<FMT>(q, qn, lane, src, out);
 }
 
 }  // namespace txp

@@ -208,8 +208,8 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         TXP_CUDA(cudaMemcpyToSymbol(g_alpha_lattice, TXP_ALPHA_LATTICE, sizeof(TXP_ALPHA_LATTICE)));
         TXP_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
 #define TXP_LATTICE_ATTR(F, T, M) TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_image_smem<T, LATTICE_STAGES>()))
-        TXP_LATTICE_ATTR(BC4, 128, 6); TXP_LATTICE_ATTR(BC4, 256, 4); TXP_LATTICE_ATTR(BC4, 256, 2); TXP_LATTICE_ATTR(BC4, 256, 3);
-        TXP_LATTICE_ATTR(BC5, 128, 6); TXP_LATTICE_ATTR(BC5, 256, 4); TXP_LATTICE_ATTR(BC5, 256, 2); TXP_LATTICE_ATTR(BC5, 256, 3);
+        TXP_LATTICE_ATTR(BC4, 256, 2); TXP_LATTICE_ATTR(BC4, 640, 1); TXP_LATTICE_ATTR(BC4, 512, 1);
+        TXP_LATTICE_ATTR(BC5, 256, 2); TXP_LATTICE_ATTR(BC5, 640, 1); TXP_LATTICE_ATTR(BC5, 512, 1);
 #undef TXP_LATTICE_ATTR
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
@@ -295,11 +295,11 @@ static EncodeParams to_device_params(const txp_params* p) {
 // ---- kernel launchers -------------------------------------------------------------------------------
 static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, const txp_params* p, uint8_t* d_out, cudaStream_t st) {
     if (src.nblocks == 0) return TXP_OK;
-    if (src.nblocks > 0x7FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^31-1 blocks in one launch");
+    if (src.nblocks > 0x3FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^30-1 blocks in one launch");
     const EncodeParams e = to_device_params(p);
     if (format == BC4 || format == BC5) {
         // TXP_ALPHA_VARIANT (tuning knob): unset / 0 = lattice fast path + compacted literal path (txp_alpha_lattice.cuh);
-        // 1..5 = the literal one-thread-per-block kernel (txp_alpha.cuh) in different launch shapes, kept for A/B runs.
+        // 1..3 = the literal one-thread-per-block kernel (txp_alpha.cuh) in different launch shapes, kept for A/B runs.
         static const int variant = [] { const char* e = getenv("TXP_ALPHA_VARIANT"); return e ? atoi(e) : 0; }();
 #define TXP_ALPHA_LAUNCH(F, T, M) alpha_encode_kernel<F, T, M><<<(unsigned)((src.nblocks + (T) - 1) / (T)), T, 0, st>>>(src, d_out)
 #define TXP_LATTICE_LAUNCH(F, T, M)                                                                                   \
@@ -307,7 +307,7 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         const uint32_t ntiles = (uint32_t)((src.nblocks + 31) / 32);                                                  \
         const uint32_t need = (ntiles + (T) / 32 - 1) / ((T) / 32), cap = (uint32_t)ctx.sm_count * (M);               \
         const uint32_t grid = need < cap ? need : cap;                                                                \
-        if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged) {                                           \
+        if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged && (uint64_t)src.w * src.h * 4 < 0xF0000000ull) {                                           \
             /* plain aligned image: cp.async-staged kernel; per-iteration block stride as (quotient, remainder) of bw */ \
             const uint64_t step = (uint64_t)grid * ((T) / 32) * 32;                                                   \
             alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES><<<grid, T, lattice_image_smem<T, LATTICE_STAGES>(), st>>>(             \
@@ -317,29 +317,25 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         }                                                                                                             \
     } while (0)
         static const bool alpha_staged = [] { const char* e = getenv("TXP_ALPHA_STAGED"); return !e || atoi(e) != 0; }();
+        // launch shapes measured with tools/micro/alpha_ab.cu (profiles/README.md): one 512-thread CTA per SM (16 warps,
+        // 4 per scheduler, <= 128 registers) is the fastest; warp counts that are not a multiple of 4 per SM lose 10-15 %.
         if (format == BC4) {
             switch (variant) {
             case 1: TXP_ALPHA_LAUNCH(BC4, 128, 8); break;
             case 2: TXP_ALPHA_LAUNCH(BC4, 128, 6); break;
             case 3: TXP_ALPHA_LAUNCH(BC4, 256, 3); break;
-            case 4: TXP_ALPHA_LAUNCH(BC4, 64, 16); break;
-            case 5: TXP_ALPHA_LAUNCH(BC4, 256, 4); break;
-            case 6: TXP_LATTICE_LAUNCH(BC4, 128, 6); break;
-            case 7: TXP_LATTICE_LAUNCH(BC4, 256, 4); break;
-            case 8: TXP_LATTICE_LAUNCH(BC4, 256, 2); break;
-            default: TXP_LATTICE_LAUNCH(BC4, 256, 3); break;
+            case 6: TXP_LATTICE_LAUNCH(BC4, 256, 2); break;
+            case 7: TXP_LATTICE_LAUNCH(BC4, 640, 1); break;
+            default: TXP_LATTICE_LAUNCH(BC4, 512, 1); break;
             }
         } else {
             switch (variant) {
             case 1: TXP_ALPHA_LAUNCH(BC5, 128, 8); break;
             case 2: TXP_ALPHA_LAUNCH(BC5, 128, 6); break;
             case 3: TXP_ALPHA_LAUNCH(BC5, 256, 3); break;
-            case 4: TXP_ALPHA_LAUNCH(BC5, 64, 16); break;
-            case 5: TXP_ALPHA_LAUNCH(BC5, 256, 4); break;
-            case 6: TXP_LATTICE_LAUNCH(BC5, 128, 6); break;
-            case 7: TXP_LATTICE_LAUNCH(BC5, 256, 4); break;
-            case 8: TXP_LATTICE_LAUNCH(BC5, 256, 2); break;
-            default: TXP_LATTICE_LAUNCH(BC5, 256, 3); break;
+            case 6: TXP_LATTICE_LAUNCH(BC5, 256, 2); break;
+            case 7: TXP_LATTICE_LAUNCH(BC5, 640, 1); break;
+            default: TXP_LATTICE_LAUNCH(BC5, 512, 1); break;
             }
         }
 #undef TXP_LATTICE_LAUNCH

@@ -25,7 +25,10 @@ def _tri(t, p):
 
 
 def generate(kind, width, height, seed, y0=0, y1=None, rows_per_chunk=512):
-    """Returns a (y1-y0, width, 4) uint8 array.  kind: noise_alpha | noise_opaque | smooth | r_rg."""
+    """Returns a (y1-y0, width, 4) uint8 array.  kind: noise_alpha | noise_opaque | smooth | r_rg | r_rg_smooth.
+    r_rg is uniform byte noise in R and G (every value 0..255 equally likely: 11.8 % of the 4x4 blocks contain a 0 or a 255,
+    the values the 5-point alpha book treats specially, alpha.rs:194-212); r_rg_smooth is the "smooth variant" of
+    SURVEY 8(d): two triangle-wave gradients plus 4-5 bits of noise, values 20..235 (height / normal map like)."""
     y1 = height if y1 is None else y1
     out = np.empty((y1 - y0, width, 4), dtype=np.uint8)
     for a in range(y0, y1, rows_per_chunk):
@@ -40,6 +43,13 @@ def generate(kind, width, height, seed, y0=0, y1=None, rows_per_chunk=512):
         elif kind == "r_rg":
             o[..., 0] = (h & np.uint64(255)).astype(np.uint8)
             o[..., 1] = ((h >> np.uint64(8)) & np.uint64(255)).astype(np.uint8)
+            o[..., 2] = 0
+            o[..., 3] = 255
+        elif kind == "r_rg_smooth":
+            y = np.arange(a, b, dtype=np.int64)[:, None]
+            x = np.arange(width, dtype=np.int64)[None, :]
+            o[..., 0] = (24 + (_tri(x + y // 2, 193) * 3) // 4 + ((h >> np.uint64(16)) & np.uint64(15)).astype(np.int64)).astype(np.uint8)
+            o[..., 1] = (20 + (_tri(y + x // 3, 167) * 3) // 4 + ((h >> np.uint64(24)) & np.uint64(31)).astype(np.int64)).astype(np.uint8)
             o[..., 2] = 0
             o[..., 3] = 255
         elif kind == "smooth":

@@ -56,21 +56,24 @@ def main():
     P = T.COLOUR_WEIGHTS_PERCEPTUAL
     if "bc4" in cases or "bc5" in cases or "decode" in cases:
         w = h = 16384
-        img = torch.from_numpy(synth.generate("r_rg", w, h, 4).reshape(-1)).cuda()
-        for name, fmt, bs in (("bc4", T.Format.Bc4, 8), ("bc5", T.Format.Bc5, 16)):
-            if name not in cases and "decode" not in cases:
+        for kind in ("r_rg", "r_rg_smooth", "smooth"):
+            if kind != "r_rg" and not ("bc4" in cases or "bc5" in cases):
                 continue
-            out = torch.empty((w // 4) * (h // 4) * bs, dtype=torch.uint8, device="cuda")
-            ms, best = time_kernel(lambda: enc(fmt, img, w, h, T.Params(), out), args.reps, flush)
-            if name in cases:
-                report(f"{name}_encode_r_rg", w, h, ms, best, 64 + bs)
-            if "decode" in cases:
-                dimg = torch.empty(w * h * 4, dtype=torch.uint8, device="cuda")
-                ms, best = time_kernel(lambda: dec(fmt, out, w, h, dimg), args.reps, flush)
-                report(f"{name}_decode", w, h, ms, best, 64 + bs)
-                del dimg
-            del out
-        del img
+            img = torch.from_numpy(synth.generate(kind, w, h, 4).reshape(-1)).cuda()
+            for name, fmt, bs in (("bc4", T.Format.Bc4, 8), ("bc5", T.Format.Bc5, 16)):
+                if name not in cases and "decode" not in cases:
+                    continue
+                out = torch.empty((w // 4) * (h // 4) * bs, dtype=torch.uint8, device="cuda")
+                ms, best = time_kernel(lambda: enc(fmt, img, w, h, T.Params(), out), args.reps, flush)
+                if name in cases:
+                    report(f"{name}_encode_{kind}", w, h, ms, best, 64 + bs)
+                if "decode" in cases and kind == "r_rg":
+                    dimg = torch.empty(w * h * 4, dtype=torch.uint8, device="cuda")
+                    ms, best = time_kernel(lambda: dec(fmt, out, w, h, dimg), args.reps, flush)
+                    report(f"{name}_decode", w, h, ms, best, 64 + bs)
+                    del dimg
+                del out
+            del img
     if "decode" in cases:
         w = h = 8192
         img = torch.from_numpy(synth.generate("noise_alpha", w, h, 3).reshape(-1)).cuda()
