@@ -110,3 +110,58 @@ def test_random_regular_blocks(seed):
     want = oracle_bc4(values)
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, (bad.size, values[bad[0]].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())
+
+
+# ---- narrow-range blocks (max - min <= 6, no 0 / 255, min <= 248): closed form of txp_alpha_lattice.cuh -----------------
+def emulate_narrow(values):
+    """fix_range (alpha.rs:70-77) widens both ranges: 5-point book codes lo..lo+5 (or lo+{0,1,2,3,4,6} when r == 6), 7-point
+    book every integer lo..lo+7, so err7 == 0 always and err5 == 0 unless r == 6 and a pixel sits at lo+5."""
+    v = values.astype(np.int64)
+    lo, hi = v.min(axis=1), v.max(axis=1)
+    r = hi - lo
+    assert (lo >= 1).all() and (hi <= 254).all() and (r <= 6).all() and (lo <= 248).all()
+    x = v - lo[:, None]
+    seven = (r == 6) & (x == 5).any(axis=1)                       # the only case with err5 > err7 (alpha.rs:251)
+    map5 = np.array([0, 2, 3, 4, 5, 1, 1, 0])                     # x -> index, block written (lo, hi5)
+    map7 = np.array([1, 7, 6, 5, 4, 3, 0, 0])                     # x -> index, block written swapped (lo+7, lo)
+    idx = np.where(seven[:, None], map7[x], map5[x])
+    a0 = np.where(seven, lo + 7, lo)
+    a1 = np.where(seven, lo, np.where(r < 5, lo + 5, hi))
+    bits = np.zeros(len(v), dtype=np.uint64)
+    for i in range(16):
+        bits |= idx[:, i].astype(np.uint64) << np.uint64(3 * i)
+    out = np.zeros((len(v), 8), dtype=np.uint8)
+    out[:, 0] = a0; out[:, 1] = a1
+    for k in range(6):
+        out[:, 2 + k] = ((bits >> np.uint64(8 * k)) & np.uint64(255)).astype(np.uint8)
+    return out
+
+
+def test_narrow_blocks():
+    rng = np.random.default_rng(5)
+    blocks = []
+    for lo in range(1, 249):
+        for r in range(0, 7):
+            if lo + r > 254:
+                continue
+            for rep in range(6):
+                vals = lo + rng.integers(0, r + 1, size=16)
+                vals[rng.integers(0, 16)] = lo; vals[rng.integers(0, 16)] = lo + r
+                if (vals.max() - vals.min()) != r:
+                    vals[0] = lo; vals[1] = lo + r
+                if rep == 0 and r == 6:
+                    vals[2:] = np.where(vals[2:] == lo + 5, lo + 4, vals[2:])      # r == 6 without a pixel at lo+5
+                blocks.append(vals)
+    values = np.array(blocks, dtype=np.uint8)
+    got = emulate_narrow(values)
+    want = oracle_bc4(values)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (bad.size, values[bad[0]].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())
+
+
+def test_flat_zero_and_255_blocks():
+    """all-0 and all-255 blocks have constant encodings (used as literals by the kernel)"""
+    z = oracle_bc4(np.zeros((1, 16), np.uint8))[0]
+    f = oracle_bc4(np.full((1, 16), 255, np.uint8))[0]
+    assert bytes(z).hex() == "0005000000000000"
+    assert bytes(f).hex() == "0005ffffffffffff"

@@ -85,3 +85,32 @@ def test_images(fmt, size, kind):
     got = T.Format(fmt).compress(img, w, h, T.Params())
     want = O.compress(fmt, img, w, h)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("fmt", [O.BC4, O.BC5])
+def test_narrow_and_flat_blocks(fmt):
+    """closed-form path for flat / narrow-range blocks (alpha_fit_narrow): every lo, every range 0..6, plus flat 0 / 255,
+    ranges clamped at 255 (lo > 248) and narrow ranges that touch 0 or 255 (those stay on the literal path)"""
+    import texpresso_b200 as T
+    rng = np.random.default_rng(5)
+    vals = []
+    for lo in range(0, 256):
+        for r in range(0, 7):
+            if lo + r > 255:
+                continue
+            for rep in range(3):
+                v = lo + rng.integers(0, r + 1, size=16)
+                v[rng.integers(0, 16)] = lo; v[rng.integers(0, 16)] = lo + r
+                if rep == 0 and r == 6:
+                    v = np.where(v == lo + 5, lo + 4, v)
+                vals.append(v)
+    values = np.array(vals, dtype=np.uint8)
+    n = len(values)
+    blocks = np.zeros((n, 16, 4), dtype=np.uint8)
+    blocks[:, :, 0] = values
+    blocks[:, :, 1] = values[rng.permutation(n)]
+    masks = np.full(n, 0xFFFF, np.uint32)
+    got = T.compress_blocks(fmt, blocks, masks, T.Params())
+    want = O.compress_blocks(fmt, blocks, masks)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (bad.size, blocks[bad[0], :, :2].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())

@@ -87,8 +87,51 @@ __device__ __forceinline__ int lattice_book(const uint32_t vm[16], const uint32_
     return (int)cc - 2 * (int)cv;
 }
 
+// four byte-sized 3-bit indices per word -> 48-bit index field + end points (alpha.rs:121-144)
+__device__ __forceinline__ uint2 pack_alpha_block(const uint32_t a0, const uint32_t a1, const uint32_t w[4]) {
+    uint32_t z[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t y = (w[k] | (w[k] >> 5)) & 0x003F003Fu;
+        z[k] = (y | (y >> 10)) & 0xFFFu;
+    }
+    const uint32_t g0 = z[0] | (z[1] << 12), g1 = z[2] | (z[3] << 12);
+    return make_uint2(a0 | (a1 << 8) | (g0 << 16), (g0 >> 16) | (g1 << 8));
+}
+
+// Flat and narrow-range blocks (what flat regions of real textures are made of), also in closed form:
+//  * all 0 / all 255: constant encodings (min5/max5 of empty sets, alpha.rs:215-224): 00 05 00.. / 00 05 FF..
+//  * max - min <= 6, no 0 / 255, min <= 248: fix_range (alpha.rs:70-77) widens the ranges to (lo, lo + max(r, 5)) and
+//    (lo, lo + 7); the 7-point book then holds every integer lo..lo+7 (err7 == 0) and the 5-point book lo..lo+5, or
+//    lo + {0,1,2,3,4,6} when r == 6, so err5 == 0 unless r == 6 and some pixel sits at lo + 5 -- the only case in which
+//    the 7-point block is written (alpha.rs:251).  Index = a byte LUT of x = v - lo.  tests/test_alpha_lattice.py
+//    checks this restatement against the oracle for every lo and r.
+// Everything else (0 / 255 mixed with other values, min > 248) takes the literal search.
+__device__ __forceinline__ bool alpha_is_narrow(const uint32_t lo, const uint32_t hi) {
+    return hi == 0u || lo == 255u || (lo >= 1u && hi <= 254u && hi - lo <= 6u && lo <= 248u);
+}
+__device__ __forceinline__ uint2 alpha_fit_narrow(const uint32_t lo, const uint32_t hi, const uint32_t V[4]) {
+    if (hi == 0u) return make_uint2(0x00000500u, 0u);
+    if (lo == 255u) return make_uint2(0xFFFF0500u, 0xFFFFFFFFu);
+    const uint32_t r = hi - lo;
+    uint32_t sel[4], any5 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = V[k] - lo * 0x01010101u;                       // x = v - lo per byte, 0..6
+        const uint32_t n = x | (x >> 4);                                  // byte 0: x0 | x1 << 4, byte 2: x2 | x3 << 4
+        sel[k] = prmt(n, n, 0x0020u);
+        any5 |= prmt(0u, 0x00000100u, sel[k]);                            // 1 where x == 5
+    }
+    const bool seven = r == 6u && any5 != 0u;
+    const uint32_t mlo = seven ? 0x05060701u : 0x04030200u, mhi = seven ? 0x00000304u : 0x00010105u;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = prmt(mlo, mhi, sel[k]);
+    return pack_alpha_block(seven ? lo + 7u : lo, seven ? lo : (r < 5u ? lo + 5u : lo + r), w);
+}
+
 // One channel of one fully valid block, given as vm[i] = 1.5*2^15 + v_i (fp32 bits) and V = the same 16 values as
-// packed bytes.  Returns false if the block is not regular.
+// packed bytes.  Returns true (out written) for a regular block, false for one that goes to the queue.
 __device__ __forceinline__ bool alpha_fit_lattice(const uint32_t vm[16], const uint32_t V[4], const uint4* __restrict__ tab, uint2& out) {
     // min / max on the raw bits (positive floats order like integers)
 #if TXP_LAT_MM
@@ -116,15 +159,10 @@ __device__ __forceinline__ bool alpha_fit_lattice(const uint32_t vm[16], const u
     const bool five = err5 <= err7;                                    // alpha.rs:251
     const uint32_t a0 = five ? lo : hi, a1 = five ? hi : lo;          // write_alpha_block5 as is / write_alpha_block7 swapped
     const uint32_t mhi = five ? 0x00000105u : 0x01070605u;            // slot -> index: 0 -> 0, N -> 1, s -> s + 1
-    uint32_t z[4];
+    uint32_t w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t w = prmt(0x04030200u, mhi, five ? s5[k] : s7[k]);   // four 3-bit indices, one per byte
-        const uint32_t y = (w | (w >> 5)) & 0x003F003Fu;
-        z[k] = (y | (y >> 10)) & 0xFFFu;
-    }
-    const uint32_t g0 = z[0] | (z[1] << 12), g1 = z[2] | (z[3] << 12);
-    out = make_uint2(a0 | (a1 << 8) | (g0 << 16), (g0 >> 16) | (g1 << 8));
+    for (int k = 0; k < 4; ++k) w[k] = prmt(0x04030200u, mhi, five ? s5[k] : s7[k]);   // four 3-bit indices, one per byte
+    out = pack_alpha_block(a0, a1, w);
     return true;
 }
 
@@ -173,25 +211,38 @@ __device__ __forceinline__ void alpha_fit_block(const uint32_t px[16], const uin
     }
 }
 
-// ---- per-warp queue of irregular (block, channel) items ------------------------------------------------------------
+// ---- per-warp queues of irregular (block, channel) items -----------------------------------------------------------
 // meta = block | RELOAD << 30 | channel << 31.  Fully valid blocks carry their 16 channel values as packed bytes, so
-// the literal path needs no second trip to memory; partial (edge) blocks are re-gathered with their mask (RELOAD).
-constexpr int LATTICE_QUEUE = 96;                 // <= 31 left over + 2 x 32 new items per tile
+// neither path needs a second trip to memory; partial (edge) blocks are re-gathered with their mask (RELOAD).
+// Two levels, so that the main loop pays for one ballot per channel only:
+//   queue A  <- every irregular item of a tile (ballot-compacted).  Drained 32 at a time: flat / narrow-range items are
+//               finished on the spot in closed form (~80 instructions), the others are compacted once more into
+//   queue B  <- items that need the 650-instruction literal search, which therefore always runs with full warps.
+constexpr int QUEUE_A = 96;                       // <= 31 left over + 2 x 32 new items per tile
+constexpr int QUEUE_B = 64;                       // <= 31 left over + 32 from one drain of A
 constexpr uint32_t ITEM_RELOAD = 0x40000000u, ITEM_BLOCK = 0x3FFFFFFFu;
 struct WarpQueue {
-    uint4 vals[LATTICE_QUEUE];
-    uint32_t meta[LATTICE_QUEUE];
+    uint4 a_vals[QUEUE_A];
+    uint4 b_vals[QUEUE_B];
+    uint32_t a_meta[QUEUE_A];
+    uint32_t b_meta[QUEUE_B];
 };
 
 template <int FMT>
-__device__ __noinline__ void alpha_drain_item(const BlockSource& src, uint8_t* __restrict__ out, const uint32_t meta, const uint4 V) {
+__device__ __forceinline__ void store_item(uint8_t* __restrict__ out, const uint32_t meta, const uint2 r) {
+    const uint32_t b = meta & ITEM_BLOCK, ch = meta >> 31;
+    reinterpret_cast<uint2*>(out)[FMT == BC4 ? (size_t)b : 2 * (size_t)b + ch] = r;
+}
+
+template <int FMT>
+__device__ __noinline__ void alpha_literal_item(const BlockSource& src, uint8_t* __restrict__ out, const uint32_t meta, const uint4 V) {
 #ifdef TXP_LAT_NODRAIN            // measurement only (tools/micro/alpha_ab.cu): cost of the literal path
     return;
 #endif
-    const uint32_t b = meta & ITEM_BLOCK, ch = meta >> 31;
     uint32_t v[16];
     uint2 r;
     if (meta & ITEM_RELOAD) {
+        const uint32_t b = meta & ITEM_BLOCK, ch = meta >> 31;
         uint32_t px[16], mask;
         load_block_thread(src, b, px, mask);
 #pragma unroll
@@ -203,49 +254,99 @@ __device__ __noinline__ void alpha_drain_item(const BlockSource& src, uint8_t* _
         for (int i = 0; i < 16; ++i) v[i] = (w[i >> 2] >> (8 * (i & 3))) & 255u;
         r = alpha_fit_full(v);
     }
-    reinterpret_cast<uint2*>(out)[FMT == BC4 ? (size_t)b : 2 * (size_t)b + ch] = r;
+    store_item<FMT>(out, meta, r);
 }
 
-// push this tile's irregular items (ballot-compacted), then run the literal path on full warps of queued items
+// one drain step of queue A for this lane's item (has == false: no item): closed form or hand-over to queue B
 template <int FMT>
-__device__ __forceinline__ void queue_push_drain(WarpQueue& q, uint32_t& qn, const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out,
-                                                 const uint32_t b, const bool todo0, const uint32_t reload0, const uint32_t V0[4],
-                                                 const bool todo1, const uint32_t V1[4]) {
+__device__ __forceinline__ void drain_a_step(WarpQueue& q, uint32_t& qb, const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out,
+                                             const bool has, const uint32_t meta, const uint4 V) {
+    // min / max of the 16 packed bytes as two 16-bit lanes per word (VIMNMX3.U16x2)
+    const uint32_t w[4] = {V.x, V.y, V.z, V.w};
+    const uint32_t e0 = w[0] & 0x00FF00FFu, e1 = w[1] & 0x00FF00FFu, e2 = w[2] & 0x00FF00FFu, e3 = w[3] & 0x00FF00FFu;
+    const uint32_t o0 = (w[0] >> 8) & 0x00FF00FFu, o1 = (w[1] >> 8) & 0x00FF00FFu, o2 = (w[2] >> 8) & 0x00FF00FFu, o3 = (w[3] >> 8) & 0x00FF00FFu;
+    const uint32_t mn2 = __vimin3_u16x2(__vimin3_u16x2(e0, e1, e2), __vimin3_u16x2(e3, o0, o1), __vminu2(o2, o3));
+    const uint32_t mx2 = __vimax3_u16x2(__vimax3_u16x2(e0, e1, e2), __vimax3_u16x2(e3, o0, o1), __vmaxu2(o2, o3));
+    const uint32_t lo = min(mn2 & 0xFFFFu, mn2 >> 16), hi = max(mx2 & 0xFFFFu, mx2 >> 16);
+    const bool narrow = has && !(meta & ITEM_RELOAD) && alpha_is_narrow(lo, hi);
+    if (narrow) store_item<FMT>(out, meta, alpha_fit_narrow(lo, hi, w));
+    const bool lit = has && !narrow;
+    const uint32_t ml = __ballot_sync(FULL, lit);
+    if (lit) { const uint32_t i = qb + __popc(ml & ((1u << lane) - 1u)); q.b_meta[i] = meta; q.b_vals[i] = V; }
+    qb += __popc(ml);
+    __syncwarp();
+#pragma unroll 1
+    while (qb >= 32) {
+        qb -= 32;
+        const uint32_t m = q.b_meta[qb + lane];
+        const uint4 v = q.b_vals[qb + lane];
+        __syncwarp();
+        alpha_literal_item<FMT>(src, out, m, v);
+    }
+}
+
+// push this tile's irregular items, then drain queue A while it holds a full warp of items
+template <int FMT>
+__device__ __forceinline__ void queue_push_drain(WarpQueue& q, uint32_t& qa, uint32_t& qb, const uint32_t lane, const BlockSource& src,
+                                                 uint8_t* __restrict__ out, const uint32_t b_reload,
+                                                 const bool todo0, const uint32_t V0[4], const bool todo1, const uint32_t V1[4]) {
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t m0 = __ballot_sync(FULL, todo0);
-    if (todo0) { const uint32_t i = qn + __popc(m0 & lt); q.meta[i] = b | reload0; q.vals[i] = make_uint4(V0[0], V0[1], V0[2], V0[3]); }
-    qn += __popc(m0);
+    if (todo0) { const uint32_t i = qa + __popc(m0 & lt); q.a_meta[i] = b_reload; q.a_vals[i] = make_uint4(V0[0], V0[1], V0[2], V0[3]); }
+    qa += __popc(m0);
     if (FMT == BC5) {
         const uint32_t m1 = __ballot_sync(FULL, todo1);
-        if (todo1) { const uint32_t i = qn + __popc(m1 & lt); q.meta[i] = b | reload0 | 0x80000000u; q.vals[i] = make_uint4(V1[0], V1[1], V1[2], V1[3]); }
-        qn += __popc(m1);
+        if (todo1) { const uint32_t i = qa + __popc(m1 & lt); q.a_meta[i] = b_reload | 0x80000000u; q.a_vals[i] = make_uint4(V1[0], V1[1], V1[2], V1[3]); }
+        qa += __popc(m1);
     }
     __syncwarp();
 #pragma unroll 1
-    while (qn >= 32) {
-        qn -= 32;
-        const uint32_t meta = q.meta[qn + lane];
-        const uint4 V = q.vals[qn + lane];
+    while (qa >= 32) {
+        qa -= 32;
+        const uint32_t i = qa + lane;
+        const uint32_t meta = q.a_meta[i];
+        const uint4 V = q.a_vals[i];
         __syncwarp();
-        alpha_drain_item<FMT>(src, out, meta, V);
+        drain_a_step<FMT>(q, qb, lane, src, out, true, meta, V);
     }
 }
 
 template <int FMT>
-__device__ __forceinline__ void queue_flush(WarpQueue& q, const uint32_t qn, const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out) {
-    if (lane < qn) alpha_drain_item<FMT>(src, out, q.meta[lane], q.vals[lane]);
+__device__ __forceinline__ void queue_flush(WarpQueue& q, const uint32_t qa, uint32_t qb, const uint32_t lane, const BlockSource& src,
+                                            uint8_t* __restrict__ out) {
+    const bool has = lane < qa;
+    const uint32_t i = has ? lane : 0u;
+    drain_a_step<FMT>(q, qb, lane, src, out, has, q.a_meta[i], q.a_vals[i]);
+    if (lane < qb) alpha_literal_item<FMT>(src, out, q.b_meta[lane], q.b_vals[lane]);      // qb < 32 after drain_a_step
+}
+
+// the per-block body shared by both kernels: px -> outputs for regular channels, queue items for the rest
+template <int FMT>
+__device__ __forceinline__ void alpha_block_body(const uint32_t px[16], const uint4* __restrict__ tab, uint8_t* __restrict__ out, const uint32_t b,
+                                                 bool& todo0, uint32_t VR[4], bool& todo1, uint32_t VG[4]) {
+    uint2 r0, r1;
+    bool ok0, ok1;
+    alpha_fit_block<FMT>(px, tab, ok0, r0, VR, ok1, r1, VG);
+    todo0 = !ok0; todo1 = !ok1;
+    uint2* o2 = reinterpret_cast<uint2*>(out) + (FMT == BC4 ? (size_t)b : 2 * (size_t)b);
+    if (ok0) o2[0] = r0;
+    if (FMT == BC5 && ok1) o2[1] = r1;
 }
 
 // ---- general kernel: list mode, mip chains, unaligned widths (direct loads) -----------------------------------------
+template <int THREADS>
+constexpr size_t lattice_smem() { return 512 * sizeof(uint4) + (THREADS / 32) * sizeof(WarpQueue); }
+
 template <int FMT, int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_kernel(const __grid_constant__ BlockSource src, uint8_t* __restrict__ out, const uint32_t ntiles) {
-    __shared__ uint4 tab[512];
-    __shared__ WarpQueue queues[THREADS / 32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* tab = reinterpret_cast<uint4*>(smem_raw);
+    WarpQueue* queues = reinterpret_cast<WarpQueue*>(tab + 512);
     for (int i = threadIdx.x; i < 512; i += THREADS) tab[i] = g_alpha_lattice[i];
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpQueue& q = queues[warp];
-    uint32_t qn = 0;
+    uint32_t qa = 0, qb = 0;
     const uint32_t stride = gridDim.x * (THREADS / 32);
 #pragma unroll 1
     for (uint32_t tile = blockIdx.x * (THREADS / 32) + warp; tile < ntiles; tile += stride) {
@@ -256,20 +357,14 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_kernel(const 
             uint32_t px[16], mask;
             load_block_thread(src, b, px, mask);
             if (mask == 0xFFFFu) {
-                uint2 r0, r1;
-                bool ok0, ok1;
-                alpha_fit_block<FMT>(px, tab, ok0, r0, VR, ok1, r1, VG);
-                todo0 = !ok0; todo1 = !ok1;
-                uint2* o2 = reinterpret_cast<uint2*>(out) + (FMT == BC4 ? (size_t)b : 2 * (size_t)b);
-                if (ok0) o2[0] = r0;
-                if (FMT == BC5 && ok1) o2[1] = r1;
+                alpha_block_body<FMT>(px, tab, out, b, todo0, VR, todo1, VG);
             } else {
                 todo0 = true; todo1 = FMT == BC5; reload = ITEM_RELOAD;
             }
         }
-        queue_push_drain<FMT>(q, qn, lane, src, out, b, todo0, reload, VR, todo1, VG);
+        queue_push_drain<FMT>(q, qa, qb, lane, src, out, b | reload, todo0, VR, todo1, VG);
     }
-    queue_flush<FMT>(q, qn, lane, src, out);
+    queue_flush<FMT>(q, qa, qb, lane, src, out);
 }
 
 // ---- image-mode kernel: same algorithm, block rows staged through shared memory with cp.async ----------------------
@@ -300,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpQueue& q = queues[warp];
-    uint32_t qn = 0;
+    uint32_t qa = 0, qb = 0;
     const uint32_t stride = gridDim.x * (THREADS / 32);
     const uint32_t bw = src.bw, nblocks = (uint32_t)src.nblocks, full_rows = src.h >> 2;   // block rows with 4 pixel rows
     const uint32_t pitch = src.w * 4;                                                 // image bytes < 2^32 (checked by the host)
@@ -343,21 +438,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(
             const uint4* sp = my + st * (4 * 32);
 #pragma unroll
             for (int r = 0; r < 4; ++r) { const uint4 v = sp[r * 32]; px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w; }
-            uint2 r0, r1;
-            bool ok0, ok1;
-            alpha_fit_block<FMT>(px, tab, ok0, r0, VR, ok1, r1, VG);
-            todo0 = !ok0; todo1 = !ok1;
-            uint2* o2 = reinterpret_cast<uint2*>(out) + (FMT == BC4 ? (size_t)b : 2 * (size_t)b);
-            if (ok0) o2[0] = r0;
-            if (FMT == BC5 && ok1) o2[1] = r1;
+            alpha_block_body<FMT>(px, tab, out, b, todo0, VR, todo1, VG);
         } else if (b < nblocks) {                                                     // partial bottom row
             todo0 = true; todo1 = FMT == BC5; reload = ITEM_RELOAD;
         }
-        queue_push_drain<FMT>(q, qn, lane, src, out, b, todo0, reload, VR, todo1, VG);
+        queue_push_drain<FMT>(q, qa, qb, lane, src, out, b | reload, todo0, VR, todo1, VG);
         st = st + 1 == STAGES ? 0 : st + 1;
     }
     cp_async_wait<0>();
-    queue_flush<FMT>(q, qn, lane, src, out);
+    queue_flush<FMT>(q, qa, qb, lane, src, out);
 }
 
 }  // namespace txp

@@ -207,7 +207,9 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         static_assert(sizeof(TXP_ALPHA_LATTICE) == 512 * sizeof(uint4), "alpha lattice table size");
         TXP_CUDA(cudaMemcpyToSymbol(g_alpha_lattice, TXP_ALPHA_LATTICE, sizeof(TXP_ALPHA_LATTICE)));
         TXP_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
-#define TXP_LATTICE_ATTR(F, T, M) TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_image_smem<T, LATTICE_STAGES>()))
+#define TXP_LATTICE_ATTR(F, T, M)                                                                                                                                      \
+        TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_image_smem<T, LATTICE_STAGES>())); \
+        TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_kernel<F, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_smem<T>()))
         TXP_LATTICE_ATTR(BC4, 256, 2); TXP_LATTICE_ATTR(BC4, 640, 1); TXP_LATTICE_ATTR(BC4, 512, 1);
         TXP_LATTICE_ATTR(BC5, 256, 2); TXP_LATTICE_ATTR(BC5, 640, 1); TXP_LATTICE_ATTR(BC5, 512, 1);
 #undef TXP_LATTICE_ATTR
@@ -313,7 +315,7 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
             alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES><<<grid, T, lattice_image_smem<T, LATTICE_STAGES>(), st>>>(             \
                 src, d_out, ntiles, (uint32_t)(step / src.bw), (uint32_t)(step % src.bw));                            \
         } else {                                                                                                      \
-            alpha_lattice_kernel<F, T, M><<<grid, T, 0, st>>>(src, d_out, ntiles);                                    \
+            alpha_lattice_kernel<F, T, M><<<grid, T, lattice_smem<T>(), st>>>(src, d_out, ntiles);                                    \
         }                                                                                                             \
     } while (0)
         static const bool alpha_staged = [] { const char* e = getenv("TXP_ALPHA_STAGED"); return !e || atoi(e) != 0; }();
