@@ -165,3 +165,139 @@ def test_flat_zero_and_255_blocks():
     f = oracle_bc4(np.full((1, 16), 255, np.uint8))[0]
     assert bytes(z).hex() == "0005000000000000"
     assert bytes(f).hex() == "0005ffffffffffff"
+
+
+# ---- "one-sided" blocks: zeros (or 255s) next to ordinary values -- semi-lattice path of txp_alpha_lattice.cuh -----------
+def semi_class(values):
+    """0 = not eligible, 1 = zero side (zeros present, no 255), 2 = 255 side.  Mirrors alpha_semi_class()."""
+    v = values.astype(np.int64)
+    z = (v == 0).any(axis=1); f = (v == 255).any(axis=1)
+    inner = (v != 0) & (v != 255)
+    has = inner.any(axis=1)
+    m = np.where(inner, v, 999).min(axis=1); M = np.where(inner, v, -1).max(axis=1)
+    ok = has & (z ^ f) & (M - m >= 7)
+    c1 = M // 7                                              # first interpolant of the 7-point lattice (0, M)
+    c6 = m + (6 * (255 - m)) // 7                            # last interpolant of the lattice (m, 255)
+    okz = ok & z & (m <= c1)
+    okf = ok & f & (M >= c6)
+    return np.where(okz, 1, np.where(okf, 2, 0)), m, M
+
+
+def emulate_semi(values, tab, side):
+    v = values.astype(np.int64)
+    inner = (v != 0) & (v != 255)
+    m = np.where(inner, v, 999).min(axis=1); M = np.where(inner, v, -1).max(axis=1)
+    r5 = M - m
+    lo7 = np.zeros_like(m) if side == 1 else m
+    hi7 = M if side == 1 else np.full_like(M, 255)
+    r7 = hi7 - lo7
+    row5, row7 = tab[r5], tab[r7]
+    a5, b5 = f32(row5[:, 0]), f32(row5[:, 1])
+    a7, b7 = f32(row7[:, 4]), f32(row7[:, 5])
+    offs5 = np.stack([(row5[:, 2 + k // 4] >> (8 * (k % 4))) & 255 for k in range(8)], axis=1).astype(np.int64)
+    offs7 = np.stack([(row7[:, 6 + k // 4] >> (8 * (k % 4))) & 255 for k in range(8)], axis=1).astype(np.int64)
+    # book 5: lattice (m, r5); the special pixels are sent to the slot-6 / slot-7 centres
+    x6 = (m - b5) + 6.0 / a5; x7 = (m - b5) + 7.0 / a5
+    v5 = np.where(v == 0, x6[:, None], np.where(v == 255, x7[:, None], v.astype(np.float64)))
+    s5 = np.rint((v5 - (m - b5)[:, None]) * a5[:, None]).astype(np.int64)
+    lut5 = m[:, None] + offs5
+    lut5[:, 6] = 0; lut5[:, 7] = 255
+    c5 = np.take_along_axis(lut5, s5, axis=1)
+    e5 = ((c5 - v) ** 2).sum(axis=1)
+    # book 7: lattice (lo7, r7) from the hi end; E0 = m / E1 = M replace the end codes, pixels they win are moved to the ends
+    lut7 = hi7[:, None] - offs7
+    f = lo7[:, None] + (np.arange(8)[None, :] * r7[:, None]) // 7            # interpolants c_i = lo7 + floor(i r7 / 7)
+    if side == 1:
+        c1, c2 = f[:, 1], f[:, 2]
+        cup = np.where(c1 > m, c1, c2)
+        B0 = (m + cup) // 2
+        v7 = np.where(v <= B0[:, None], 0, v)
+        lut7[:, 7] = m
+    else:
+        c6, c5i = f[:, 6], f[:, 5]
+        cdn = np.where(c6 < M, c6, c5i)
+        A1 = -((-(M + cdn)) // 2)
+        v7 = np.where(v >= A1[:, None], 255, v)
+        lut7[:, 0] = M
+    s7 = np.rint((v7 - (hi7 + b7)[:, None]) * -a7[:, None]).astype(np.int64)
+    assert s5.min() >= 0 and s5.max() <= 7 and s7.min() >= 0 and s7.max() <= 7
+    c7 = np.take_along_axis(lut7, s7, axis=1)
+    e7 = ((c7 - v) ** 2).sum(axis=1)
+    five = e5 <= e7
+    map5 = np.array([0, 2, 3, 4, 5, 1, 6, 7]); map7 = np.array([0, 2, 3, 4, 5, 6, 7, 1])
+    idx = np.where(five[:, None], map5[s5], map7[s7])
+    a0 = np.where(five, m, hi7); a1 = np.where(five, M, lo7)
+    bits = np.zeros(len(v), dtype=np.uint64)
+    for i in range(16):
+        bits |= idx[:, i].astype(np.uint64) << np.uint64(3 * i)
+    out = np.zeros((len(v), 8), dtype=np.uint8)
+    out[:, 0] = a0; out[:, 1] = a1
+    for k in range(6):
+        out[:, 2 + k] = ((bits >> np.uint64(8 * k)) & np.uint64(255)).astype(np.uint8)
+    return out
+
+
+def _one_sided_corpus(seed, n):
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(1, 248, size=n)
+    hi = np.minimum(254, lo + rng.integers(7, 254, size=n))
+    vals = (lo[:, None] + (rng.random((n, 16)) * (hi - lo + 1)[:, None]).astype(np.int64)).clip(1, 254)
+    third = n // 3
+    vals[:third] = rng.integers(1, 255, size=(third, 16))                      # plain noise
+    vals[third:2 * third] = (lo[third:2 * third, None] + np.round(rng.integers(0, 15, size=(third, 16)) * (hi - lo)[third:2 * third, None] / 14.0)).clip(1, 254)
+    special = np.where(rng.random(n) < 0.5, 0, 255)
+    k = rng.integers(1, 5, size=n)
+    for j in range(4):
+        pos = rng.integers(0, 16, size=n)
+        sel = k > j
+        vals[np.nonzero(sel)[0], pos[sel]] = special[sel]
+    return vals.astype(np.uint8)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_one_sided_blocks(seed):
+    tab = load_table()
+    values = _one_sided_corpus(seed, 90000)
+    cls, m, M = semi_class(values)
+    assert (cls == 1).sum() > 5000 and (cls == 2).sum() > 5000
+    for side in (1, 2):
+        sub = values[cls == side]
+        got = emulate_semi(sub, tab, side)
+        want = oracle_bc4(sub)
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (side, bad.size, len(sub), sub[bad[0]].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())
+
+
+def _swept_one_sided():
+    rng = np.random.default_rng(3)
+    blocks = []
+    for M in range(8, 255, 3):
+        for m in range(1, M // 7 + 1):
+            if M - m < 7:
+                continue
+            xs = np.arange(m, M + 1)
+            for c in range(0, len(xs), 13 * 4):                 # a quarter of the chunks: keeps the CPU suite short
+                fill = np.resize(xs[c:c + 13], 13)
+                blocks.append(rng.permutation(np.concatenate(([0, m, M], fill))))
+    for m in range(1, 247, 2):
+        c6 = m + (6 * (255 - m)) // 7
+        for M in range(max(c6, m + 7), 255):
+            xs = np.arange(m, M + 1)
+            c = int(rng.integers(0, max(1, len(xs) - 13)))
+            fill = np.resize(xs[c:c + 13], 13)
+            blocks.append(rng.permutation(np.concatenate(([255, m, M], fill))))
+    return np.array(blocks, dtype=np.uint8)
+
+
+def test_one_sided_blocks_swept():
+    """every eligible (m, M) pair of the zero side (stride 3 in M) and of the 255 side, the 13 free pixels sweeping [m, M]"""
+    tab = load_table()
+    values = _swept_one_sided()
+    cls, _, _ = semi_class(values)
+    assert (cls > 0).all()
+    for side in (1, 2):
+        sub = values[cls == side]
+        got = emulate_semi(sub, tab, side)
+        want = oracle_bc4(sub)
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (side, bad.size, len(sub), sub[bad[0]].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())

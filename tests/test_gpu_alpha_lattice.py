@@ -114,3 +114,22 @@ def test_narrow_and_flat_blocks(fmt):
     want = O.compress_blocks(fmt, blocks, masks)
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, (bad.size, blocks[bad[0], :, :2].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())
+
+
+@pytest.mark.parametrize("fmt", [O.BC4, O.BC5])
+def test_one_sided_blocks(fmt):
+    """semi-lattice path (zeros or 255s next to ordinary values): the corpora of tests/test_alpha_lattice.py on the GPU,
+    including blocks that fail its side conditions and fall through to the literal search"""
+    import texpresso_b200 as T
+    from tests.test_alpha_lattice import _one_sided_corpus, _swept_one_sided
+    values = np.concatenate([_one_sided_corpus(21, 60000), _swept_one_sided()])
+    n = len(values)
+    rng = np.random.default_rng(9)
+    blocks = np.zeros((n, 16, 4), dtype=np.uint8)
+    blocks[:, :, 0] = values
+    blocks[:, :, 1] = values[rng.permutation(n)]
+    masks = np.full(n, 0xFFFF, np.uint32)
+    got = T.compress_blocks(fmt, blocks, masks, T.Params())
+    want = O.compress_blocks(fmt, blocks, masks)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (bad.size, blocks[bad[0], :, :2].tolist(), bytes(got[bad[0]]).hex(), bytes(want[bad[0]]).hex())

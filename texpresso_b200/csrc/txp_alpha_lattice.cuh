@@ -42,6 +42,9 @@ __device__ uint4 g_alpha_lattice[512];            // TXP_ALPHA_LATTICE (alpha_la
 #ifndef TXP_LAT_VMR
 #define TXP_LAT_VMR 0      // R channel -> fp32 mantissa: 0 = PRMT, 1 = SHF + LOP3, 2 = LOP3 + IMAD
 #endif
+#ifndef TXP_LAT_SEMI
+#define TXP_LAT_SEMI 1      // 1: one-sided (zeros or 255s present) blocks take the semi-lattice path; 0: literal search
+#endif
 #ifndef TXP_LAT_MM
 #define TXP_LAT_MM 0       // min / max: 0 = VIMNMX3 trees, 1 = two-input VIMNMX
 #endif
@@ -213,19 +216,22 @@ __device__ __forceinline__ void alpha_fit_block(const uint32_t px[16], const uin
 
 // ---- per-warp queues of irregular (block, channel) items -----------------------------------------------------------
 // meta = block | RELOAD << 30 | channel << 31.  Fully valid blocks carry their 16 channel values as packed bytes, so
-// neither path needs a second trip to memory; partial (edge) blocks are re-gathered with their mask (RELOAD).
+// no path needs a second trip to memory; partial (edge) blocks are re-gathered with their mask (RELOAD).
 // Two levels, so that the main loop pays for one ballot per channel only:
-//   queue A  <- every irregular item of a tile (ballot-compacted).  Drained 32 at a time: flat / narrow-range items are
-//               finished on the spot in closed form (~80 instructions), the others are compacted once more into
-//   queue B  <- items that need the 650-instruction literal search, which therefore always runs with full warps.
+//   queue A   <- every irregular item of a tile (ballot-compacted).  Drained 32 at a time: flat / narrow-range items
+//                are finished on the spot in closed form (~80 instructions), the others are compacted once more into
+//   queue Z/F <- "one-sided" items: zeros (or 255s) next to ordinary values -> semi-lattice path (alpha_semi_item);
+//   queue L   <- everything else -> the 650-instruction literal search (alpha_literal_item).
+// Every second-level queue is drained 32 items at a time, so each path always runs with full warps.
 constexpr int QUEUE_A = 96;                       // <= 31 left over + 2 x 32 new items per tile
-constexpr int QUEUE_B = 64;                       // <= 31 left over + 32 from one drain of A
+constexpr int QUEUE_B = 64;                       // <= 31 left over + 32 from one drain step
+constexpr int QZ = 0, QF = 1, QL = 2;
 constexpr uint32_t ITEM_RELOAD = 0x40000000u, ITEM_BLOCK = 0x3FFFFFFFu;
 struct WarpQueue {
     uint4 a_vals[QUEUE_A];
-    uint4 b_vals[QUEUE_B];
+    uint4 b_vals[3][QUEUE_B];
     uint32_t a_meta[QUEUE_A];
-    uint32_t b_meta[QUEUE_B];
+    uint32_t b_meta[3][QUEUE_B];
 };
 
 template <int FMT>
@@ -257,10 +263,132 @@ __device__ __noinline__ void alpha_literal_item(const BlockSource& src, uint8_t*
     store_item<FMT>(out, meta, r);
 }
 
-// one drain step of queue A for this lane's item (has == false: no item): closed form or hand-over to queue B
+// ---- semi-lattice path: zeros (ZSIDE) or 255s (!ZSIDE) next to ordinary values ---------------------------------------
+// With m / M the smallest / largest value that is neither 0 nor 255 and M - m >= 7 (no fix_range, alpha.rs:70-77):
+//  * 5-point book (alpha.rs:227-234) = lattice (m, M - m) + the codes 0 and 255, which are exact for the special pixels:
+//    those pixels are moved to the centres of the unused slots 6 / 7, whose codebook bytes are 0 / 255 (indices 6 / 7).
+//  * 7-point book (alpha.rs:237-242, quirk Q1) = the interpolants of the lattice (0, M) resp. (m, 255) plus E0 = m, E1 = M.
+//    One end is regular; at the other the end code (0 resp. 255) is replaced by E0 resp. E1.  E0 wins exactly the values
+//    <= B0 = floor((m + c_up) / 2), c_up = the smallest interpolant > m (E0 has index 0: ties go to it), and the zero
+//    pixels too if m <= c_1; E1 wins the values >= A1 = ceil((M + c_dn) / 2), c_dn = the largest interpolant < M, and the
+//    255 pixels if M >= c_6.  Those pixels are moved to the end of the lattice, whose codebook byte is patched to E0 / E1.
+// Blocks that fail the side conditions (M - m < 7, m > c_1, M < c_6) return false -> literal queue.
+// tests/test_alpha_lattice.py restates this in numpy and checks it against the oracle (random + swept corpora).
+template <bool ZSIDE>
+__device__ __forceinline__ bool alpha_fit_semi(const uint32_t w[4], const uint4* __restrict__ tab, uint2& out) {
+    uint32_t vm[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vm[i] = prmt(MAGIC15, w[i >> 2], 0x3240u + 0x10u * (i & 3));
+    constexpr uint32_t K255 = MAGIC15 | 0xFF00u;
+    // m / M over the ordinary values: the special value wraps to the top of the unsigned range and never wins the min
+    uint32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = ZSIDE ? vm[i] - (MAGIC15 + 0x100u) : (MAGIC15 | 0xFE00u) - vm[i];
+    uint32_t tmin = __vimin3_u32(t[0], t[1], t[2]);
+    uint32_t other = ZSIDE ? __vimax3_u32(vm[0], vm[1], vm[2]) : __vimin3_u32(vm[0], vm[1], vm[2]);
+#pragma unroll
+    for (int i = 3; i < 15; i += 2) {
+        tmin = __vimin3_u32(tmin, t[i], t[i + 1]);
+        other = ZSIDE ? __vimax3_u32(other, vm[i], vm[i + 1]) : __vimin3_u32(other, vm[i], vm[i + 1]);
+    }
+    tmin = min(tmin, t[15]);
+    other = ZSIDE ? max(other, vm[15]) : min(other, vm[15]);
+    const uint32_t m_vm = ZSIDE ? tmin + (MAGIC15 + 0x100u) : other, M_vm = ZSIDE ? other : (MAGIC15 | 0xFE00u) - tmin;
+    const uint32_t m = (m_vm >> 8) & 255u, M = (M_vm >> 8) & 255u;
+    const uint32_t r5 = M - m;
+    const uint32_t lo7 = ZSIDE ? 0u : m, hi7 = ZSIDE ? M : 255u, r7 = hi7 - lo7;
+    if (M_vm < m_vm + (7u << 8)) return false;
+    if (ZSIDE ? (7u * m > M) : (M < m + ((6u * (255u - m) * 9363u) >> 16))) return false;      // m <= c_1  /  M >= c_6
+
+    const uint4 e5 = tab[2 * r5], e7 = tab[2 * r7 + 1];
+    uint32_t s5[4], s7[4], vx[16];
+    // ---- 5-point book
+    const float a5 = __uint_as_float(e5.x), origin5 = __fsub_rn(__uint_as_float(m_vm), __uint_as_float(e5.y));
+    const float xs = __fadd_rn(origin5, __fdividef(ZSIDE ? 6.0f : 7.0f, a5));        // centre of slot 6 / 7
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vx[i] = vm[i] == (ZSIDE ? MAGIC15 : K255) ? __float_as_uint(xs) : vm[i];
+    const int err5 = lattice_book(vx, w, origin5, a5, e5.z + m * 0x01010101u, ((e5.w + m * 0x01010101u) & 0x0000FFFFu) | 0xFF000000u, s5);
+    // ---- 7-point book, from the hi end
+    uint32_t clo = hi7 * 0x01010101u - e7.z, chi = hi7 * 0x01010101u - e7.w;       // slot 0 = hi7, 1..6 = c_6..c_1, 7 = lo7
+    if (ZSIDE) {
+        const uint32_t c1 = (chi >> 16) & 255u, c2 = (chi >> 8) & 255u;
+        const uint32_t b0_vm = MAGIC15 | (((m + (c1 > m ? c1 : c2)) >> 1) << 8);
+        chi = (chi & 0x00FFFFFFu) | (m << 24);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) vx[i] = vm[i] <= b0_vm ? MAGIC15 : vm[i];
+    } else {
+        const uint32_t c6 = (clo >> 8) & 255u, c5 = (clo >> 16) & 255u;
+        const uint32_t a1_vm = MAGIC15 | (((M + (c6 < M ? c6 : c5) + 1u) >> 1) << 8);
+        clo = (clo & 0xFFFFFF00u) | M;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) vx[i] = vm[i] >= a1_vm ? K255 : vm[i];
+    }
+    const float origin7 = __fadd_rn(__uint_as_float(MAGIC15 | (hi7 << 8)), __uint_as_float(e7.y));
+    const int err7 = lattice_book(vx, w, origin7, -__uint_as_float(e7.x), clo, chi, s7);
+    const bool five = err5 <= err7;                                    // alpha.rs:251
+    const uint32_t mhi = five ? 0x07060105u : 0x01070605u;
+    uint32_t iw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) iw[k] = prmt(0x04030200u, mhi, five ? s5[k] : s7[k]);
+    out = pack_alpha_block(five ? m : hi7, five ? M : lo7, iw);
+    return true;
+}
+
+template <int FMT, bool ZSIDE>
+__device__ __noinline__ bool alpha_semi_item(uint8_t* __restrict__ out, const uint4* __restrict__ tab, const uint32_t meta, const uint4 V) {
+    const uint32_t w[4] = {V.x, V.y, V.z, V.w};
+    uint2 r;
+    if (!alpha_fit_semi<ZSIDE>(w, tab, r)) return false;
+    store_item<FMT>(out, meta, r);
+    return true;
+}
+
+// compact the lanes with `take` into second-level queue `which`
+__device__ __forceinline__ void queue_b_push(WarpQueue& q, uint32_t (&qb)[3], const int which, const uint32_t lane, const bool take,
+                                             const uint32_t meta, const uint4 V) {
+    const uint32_t mk = __ballot_sync(FULL, take);
+    if (take) { const uint32_t i = qb[which] + __popc(mk & ((1u << lane) - 1u)); q.b_meta[which][i] = meta; q.b_vals[which][i] = V; }
+    qb[which] += __popc(mk);
+    __syncwarp();
+}
+
 template <int FMT>
-__device__ __forceinline__ void drain_a_step(WarpQueue& q, uint32_t& qb, const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out,
-                                             const bool has, const uint32_t meta, const uint4 V) {
+__device__ __forceinline__ void drain_literal(WarpQueue& q, uint32_t (&qb)[3], const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out,
+                                              const bool flush) {
+#pragma unroll 1
+    while (qb[QL] >= 32 || (flush && qb[QL] > 0)) {
+        const uint32_t n = min(qb[QL], 32u);
+        qb[QL] -= n;
+        const bool has = lane < n;
+        const uint32_t m = q.b_meta[QL][qb[QL] + (has ? lane : 0u)];
+        const uint4 v = q.b_vals[QL][qb[QL] + (has ? lane : 0u)];
+        __syncwarp();
+        if (has) alpha_literal_item<FMT>(src, out, m, v);
+    }
+}
+
+template <int FMT, bool ZSIDE>
+__device__ __forceinline__ void drain_semi(WarpQueue& q, uint32_t (&qb)[3], const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out,
+                                           const uint4* __restrict__ tab, const bool flush) {
+    constexpr int W = ZSIDE ? QZ : QF;
+#pragma unroll 1
+    while (qb[W] >= 32 || (flush && qb[W] > 0)) {
+        const uint32_t n = min(qb[W], 32u);
+        qb[W] -= n;
+        const bool has = lane < n;
+        const uint32_t m = q.b_meta[W][qb[W] + (has ? lane : 0u)];
+        const uint4 v = q.b_vals[W][qb[W] + (has ? lane : 0u)];
+        __syncwarp();
+        const bool done = has && alpha_semi_item<FMT, ZSIDE>(out, tab, m, v);
+        queue_b_push(q, qb, QL, lane, has && !done, m, v);                // side conditions failed -> literal search
+        drain_literal<FMT>(q, qb, lane, src, out, false);
+    }
+}
+
+// one drain step of queue A for this lane's item (has == false: no item): closed form or hand-over to a second-level queue
+template <int FMT>
+__device__ __forceinline__ void drain_a_step(WarpQueue& q, uint32_t (&qb)[3], const uint32_t lane, const BlockSource& src, uint8_t* __restrict__ out,
+                                             const uint4* __restrict__ tab, const bool has, const uint32_t meta, const uint4 V) {
     // min / max of the 16 packed bytes as two 16-bit lanes per word (VIMNMX3.U16x2)
     const uint32_t w[4] = {V.x, V.y, V.z, V.w};
     const uint32_t e0 = w[0] & 0x00FF00FFu, e1 = w[1] & 0x00FF00FFu, e2 = w[2] & 0x00FF00FFu, e3 = w[3] & 0x00FF00FFu;
@@ -268,27 +396,28 @@ __device__ __forceinline__ void drain_a_step(WarpQueue& q, uint32_t& qb, const u
     const uint32_t mn2 = __vimin3_u16x2(__vimin3_u16x2(e0, e1, e2), __vimin3_u16x2(e3, o0, o1), __vminu2(o2, o3));
     const uint32_t mx2 = __vimax3_u16x2(__vimax3_u16x2(e0, e1, e2), __vimax3_u16x2(e3, o0, o1), __vmaxu2(o2, o3));
     const uint32_t lo = min(mn2 & 0xFFFFu, mn2 >> 16), hi = max(mx2 & 0xFFFFu, mx2 >> 16);
-    const bool narrow = has && !(meta & ITEM_RELOAD) && alpha_is_narrow(lo, hi);
+    const bool full = has && !(meta & ITEM_RELOAD);
+    const bool narrow = full && alpha_is_narrow(lo, hi);
     if (narrow) store_item<FMT>(out, meta, alpha_fit_narrow(lo, hi, w));
-    const bool lit = has && !narrow;
-    const uint32_t ml = __ballot_sync(FULL, lit);
-    if (lit) { const uint32_t i = qb + __popc(ml & ((1u << lane) - 1u)); q.b_meta[i] = meta; q.b_vals[i] = V; }
-    qb += __popc(ml);
-    __syncwarp();
-#pragma unroll 1
-    while (qb >= 32) {
-        qb -= 32;
-        const uint32_t m = q.b_meta[qb + lane];
-        const uint4 v = q.b_vals[qb + lane];
-        __syncwarp();
-        alpha_literal_item<FMT>(src, out, m, v);
-    }
+#if TXP_LAT_SEMI
+    const bool zs = full && !narrow && lo == 0u && hi < 255u, fs = full && !narrow && hi == 255u && lo > 0u;
+#else
+    const bool zs = false, fs = false;
+#endif
+    queue_b_push(q, qb, QL, lane, has && !narrow && !zs && !fs, meta, V);
+    drain_literal<FMT>(q, qb, lane, src, out, false);
+#if TXP_LAT_SEMI
+    queue_b_push(q, qb, QZ, lane, zs, meta, V);
+    drain_semi<FMT, true>(q, qb, lane, src, out, tab, false);
+    queue_b_push(q, qb, QF, lane, fs, meta, V);
+    drain_semi<FMT, false>(q, qb, lane, src, out, tab, false);
+#endif
 }
 
 // push this tile's irregular items, then drain queue A while it holds a full warp of items
 template <int FMT>
-__device__ __forceinline__ void queue_push_drain(WarpQueue& q, uint32_t& qa, uint32_t& qb, const uint32_t lane, const BlockSource& src,
-                                                 uint8_t* __restrict__ out, const uint32_t b_reload,
+__device__ __forceinline__ void queue_push_drain(WarpQueue& q, uint32_t& qa, uint32_t (&qb)[3], const uint32_t lane, const BlockSource& src,
+                                                 uint8_t* __restrict__ out, const uint4* __restrict__ tab, const uint32_t b_reload,
                                                  const bool todo0, const uint32_t V0[4], const bool todo1, const uint32_t V1[4]) {
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t m0 = __ballot_sync(FULL, todo0);
@@ -307,17 +436,21 @@ __device__ __forceinline__ void queue_push_drain(WarpQueue& q, uint32_t& qa, uin
         const uint32_t meta = q.a_meta[i];
         const uint4 V = q.a_vals[i];
         __syncwarp();
-        drain_a_step<FMT>(q, qb, lane, src, out, true, meta, V);
+        drain_a_step<FMT>(q, qb, lane, src, out, tab, true, meta, V);
     }
 }
 
 template <int FMT>
-__device__ __forceinline__ void queue_flush(WarpQueue& q, const uint32_t qa, uint32_t qb, const uint32_t lane, const BlockSource& src,
-                                            uint8_t* __restrict__ out) {
+__device__ __forceinline__ void queue_flush(WarpQueue& q, const uint32_t qa, uint32_t (&qb)[3], const uint32_t lane, const BlockSource& src,
+                                            uint8_t* __restrict__ out, const uint4* __restrict__ tab) {
     const bool has = lane < qa;
     const uint32_t i = has ? lane : 0u;
-    drain_a_step<FMT>(q, qb, lane, src, out, has, q.a_meta[i], q.a_vals[i]);
-    if (lane < qb) alpha_literal_item<FMT>(src, out, q.b_meta[lane], q.b_vals[lane]);      // qb < 32 after drain_a_step
+    drain_a_step<FMT>(q, qb, lane, src, out, tab, has, q.a_meta[i], q.a_vals[i]);
+#if TXP_LAT_SEMI
+    drain_semi<FMT, true>(q, qb, lane, src, out, tab, true);
+    drain_semi<FMT, false>(q, qb, lane, src, out, tab, true);
+#endif
+    drain_literal<FMT>(q, qb, lane, src, out, true);
 }
 
 // the per-block body shared by both kernels: px -> outputs for regular channels, queue items for the rest
@@ -346,7 +479,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_kernel(const 
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpQueue& q = queues[warp];
-    uint32_t qa = 0, qb = 0;
+    uint32_t qa = 0, qb[3] = {0, 0, 0};
     const uint32_t stride = gridDim.x * (THREADS / 32);
 #pragma unroll 1
     for (uint32_t tile = blockIdx.x * (THREADS / 32) + warp; tile < ntiles; tile += stride) {
@@ -362,9 +495,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_kernel(const 
                 todo0 = true; todo1 = FMT == BC5; reload = ITEM_RELOAD;
             }
         }
-        queue_push_drain<FMT>(q, qa, qb, lane, src, out, b | reload, todo0, VR, todo1, VG);
+        queue_push_drain<FMT>(q, qa, qb, lane, src, out, tab, b | reload, todo0, VR, todo1, VG);
     }
-    queue_flush<FMT>(q, qa, qb, lane, src, out);
+    queue_flush<FMT>(q, qa, qb, lane, src, out, tab);
 }
 
 // ---- image-mode kernel: same algorithm, block rows staged through shared memory with cp.async ----------------------
@@ -395,7 +528,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpQueue& q = queues[warp];
-    uint32_t qa = 0, qb = 0;
+    uint32_t qa = 0, qb[3] = {0, 0, 0};
     const uint32_t stride = gridDim.x * (THREADS / 32);
     const uint32_t bw = src.bw, nblocks = (uint32_t)src.nblocks, full_rows = src.h >> 2;   // block rows with 4 pixel rows
     const uint32_t pitch = src.w * 4;                                                 // image bytes < 2^32 (checked by the host)
@@ -442,11 +575,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(
         } else if (b < nblocks) {                                                     // partial bottom row
             todo0 = true; todo1 = FMT == BC5; reload = ITEM_RELOAD;
         }
-        queue_push_drain<FMT>(q, qa, qb, lane, src, out, b | reload, todo0, VR, todo1, VG);
+        queue_push_drain<FMT>(q, qa, qb, lane, src, out, tab, b | reload, todo0, VR, todo1, VG);
         st = st + 1 == STAGES ? 0 : st + 1;
     }
     cp_async_wait<0>();
-    queue_flush<FMT>(q, qa, qb, lane, src, out);
+    queue_flush<FMT>(q, qa, qb, lane, src, out, tab);
 }
 
 }  // namespace txp

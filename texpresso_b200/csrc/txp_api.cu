@@ -210,8 +210,8 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
 #define TXP_LATTICE_ATTR(F, T, M)                                                                                                                                      \
         TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_image_smem<T, LATTICE_STAGES>())); \
         TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_kernel<F, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_smem<T>()))
-        TXP_LATTICE_ATTR(BC4, 256, 2); TXP_LATTICE_ATTR(BC4, 640, 1); TXP_LATTICE_ATTR(BC4, 512, 1);
-        TXP_LATTICE_ATTR(BC5, 256, 2); TXP_LATTICE_ATTR(BC5, 640, 1); TXP_LATTICE_ATTR(BC5, 512, 1);
+        TXP_LATTICE_ATTR(BC4, 256, 2); TXP_LATTICE_ATTR(BC4, 512, 1);
+        TXP_LATTICE_ATTR(BC5, 256, 2); TXP_LATTICE_ATTR(BC5, 512, 1);
 #undef TXP_LATTICE_ATTR
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
         TXP_CUDA(cudaFuncSetAttribute(colour_encode_kernel<BC2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COLOUR_SMEM));
@@ -327,7 +327,6 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
             case 2: TXP_ALPHA_LAUNCH(BC4, 128, 6); break;
             case 3: TXP_ALPHA_LAUNCH(BC4, 256, 3); break;
             case 6: TXP_LATTICE_LAUNCH(BC4, 256, 2); break;
-            case 7: TXP_LATTICE_LAUNCH(BC4, 640, 1); break;
             default: TXP_LATTICE_LAUNCH(BC4, 512, 1); break;
             }
         } else {
@@ -336,7 +335,6 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
             case 2: TXP_ALPHA_LAUNCH(BC5, 128, 6); break;
             case 3: TXP_ALPHA_LAUNCH(BC5, 256, 3); break;
             case 6: TXP_LATTICE_LAUNCH(BC5, 256, 2); break;
-            case 7: TXP_LATTICE_LAUNCH(BC5, 640, 1); break;
             default: TXP_LATTICE_LAUNCH(BC5, 512, 1); break;
             }
         }

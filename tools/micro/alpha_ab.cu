@@ -71,13 +71,8 @@ template <int FMT> void run_fmt(const BlockSource& src, int sms, const char* tag
     run_shape<FMT, 256, 2, 3>(src, out, ref, sms, tag);
 #ifndef AB_ONE_SHAPE
     run_shape<FMT, 512, 1, 3>(src, out, ref, sms, tag);
-    run_shape<FMT, 512, 1, 4>(src, out, ref, sms, tag);
     run_shape<FMT, 512, 1, 2>(src, out, ref, sms, tag);
-    run_shape<FMT, 448, 1, 3>(src, out, ref, sms, tag);
-    run_shape<FMT, 576, 1, 3>(src, out, ref, sms, tag);
-    run_shape<FMT, 640, 1, 3>(src, out, ref, sms, tag);
-    run_shape<FMT, 768, 1, 3>(src, out, ref, sms, tag);
-    run_shape<FMT, 1024, 1, 2>(src, out, ref, sms, tag);
+    run_shape<FMT, 640, 1, 2>(src, out, ref, sms, tag);
 #endif
     cudaFree(out); cudaFree(ref);
 }
