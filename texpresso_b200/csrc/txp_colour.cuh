@@ -66,7 +66,7 @@ template <bool WANT_ENDPOINTS>
 __device__ __forceinline__ float solve(const float4 alphax, const float4 betax, const float ab,
                                        const float wx, const float wy, const float wz, Solution* out) {
     const float alpha2 = alphax.w, beta2 = betax.w;
-    const float factor = rcp(sub(mul(alpha2, beta2), mul(ab, ab)));
+    const float factor = rcp_normal(sub(mul(alpha2, beta2), mul(ab, ab)));
     const float av[3] = {alphax.x, alphax.y, alphax.z}, bv[3] = {betax.x, betax.y, betax.z};
     const float grid[3] = {31.0f, 63.0f, 31.0f};
     const float gridrcp[3] = {1.0f / 31.0f, 1.0f / 63.0f, 1.0f / 31.0f};
@@ -146,7 +146,7 @@ __device__ __forceinline__ float eval4_packed(const float4* S, const uint32_t E,
     upk(azw, az, alpha2);
     upk(bzw, bz, beta2);
     const float ab = mul(c29, add(p1.w, p2.w));                                      // :331
-    const float factor = rcp(sub(mul(alpha2, beta2), mul(ab, ab)));                  // :334-335
+    const float factor = rcp_normal(sub(mul(alpha2, beta2), mul(ab, ab)));           // :334-335
     float nax, nay, nbx, nby;                                                        // :336-337
     upk(sub2(mul2s(axy, beta2), mul2s(bxy, ab)), nax, nay);
     upk(sub2(mul2s(bxy, alpha2), mul2s(axy, ab)), nbx, nby);
