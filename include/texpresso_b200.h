@@ -122,7 +122,7 @@ TXP_API int txp_set_device(int device);      /* cudaSetDevice for the calling th
 TXP_API const char* txp_last_error(void);    /* thread-local description of the last failure */
 TXP_API uint64_t txp_kernel_launches(void);  /* kernels launched by this library since load */
 TXP_API const char* txp_version(void);
-TXP_API int txp_debug_set(int key, int value);   /* tuning knobs for A/B measurements; key 0: 1 = fused ClusterFit kernel */
+TXP_API int txp_debug_set(int key, int value);   /* tuning knobs for A/B measurements; key 0: ClusterFit kernel structure 0 auto, 1 fused, 2 warp per block, 3 lane per block; key 1: smallest launch (blocks) that takes the lane-per-block search in auto mode */
 
 #ifdef __cplusplus
 }

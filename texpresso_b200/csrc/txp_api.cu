@@ -4,6 +4,7 @@
 // (lib.rs:295, :138, :324), per-device contexts (streams, pinned staging, device scratch), a chunked
 // H2D -> kernel -> D2H pipeline for host buffers, block-row sharding across devices.  No CPU fallback:
 // every data path ends in a kernel launch or an error code.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +23,7 @@
 #include "txp_colour.cuh"
 #include "txp_range.cuh"
 #include "txp_cluster_setup.cuh"
+#include "txp_cluster_lane.cuh"
 #include "txp_decode.cuh"
 
 namespace txp {
@@ -132,8 +134,19 @@ __global__ void __launch_bounds__(256) mip_downsample_kernel(const uint32_t* __r
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string t_last_error;
 static std::atomic<uint64_t> g_launches{0};
-// tuning knob: 1 = single fused ClusterFit kernel, 0 = setup kernel + search kernel (default); TXP_COLOUR_VARIANT=fused
-static std::atomic<int> g_colour_fused{[] { const char* v = getenv("TXP_COLOUR_VARIANT"); return (v && std::string(v) == "fused") ? 1 : 0; }()};
+// ClusterFit kernel structure (tuning knob, txp_debug_set(0, v) or TXP_COLOUR_VARIANT=auto|fused|warp|lane):
+//  0 auto  : setup kernel + lane-per-block search (txp_cluster_lane.cuh) for ClusterFit launches of at least
+//            g_lane_min_blocks blocks, setup kernel + warp-per-block search otherwise (few blocks: the warp kernel has 32x
+//            the parallelism) and for IterativeClusterFit (per-block iteration counts differ)
+//  1 fused : the original single warp-per-block kernel          2 warp : always setup + warp-per-block search
+//  3 lane  : setup + lane-per-block search for every non-iterative ClusterFit launch
+static std::atomic<int> g_colour_variant{[] {
+    const char* v = getenv("TXP_COLOUR_VARIANT");
+    const std::string s = v ? v : "";
+    return s == "fused" ? 1 : s == "warp" ? 2 : s == "lane" ? 3 : 0;
+}()};
+static std::atomic<long long> g_lane_min_blocks{[] { const char* v = getenv("TXP_LANE_MIN_BLOCKS"); return v ? atoll(v) : 131072ll; }()};
+constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (284 B of scratch per block)
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
 
@@ -291,6 +304,9 @@ static EncodeParams to_device_params(const txp_params* p) {
     e.wx = p->weights[0]; e.wy = p->weights[1]; e.wz = p->weights[2];
     e.alpha_weighted = p->weigh_colour_by_alpha ? 1 : 0;
     e.negzero2 = 0x8000000080000000ull;
+    const float g[2] = {31.0f, 63.0f}, gr[2] = {1.0f / 31.0f, 1.0f / 63.0f};
+    memcpy(&e.grid_xy, g, 8);
+    memcpy(&e.gridrcp_xy, gr, 8);
     return e;
 }
 
@@ -349,7 +365,37 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
     } else {
         const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
         const unsigned threads = COLOUR_WARPS * 32;
-        if (g_colour_fused.load(std::memory_order_relaxed)) {                                      // single-kernel variant kept for A/B measurements
+        const int variant = g_colour_variant.load(std::memory_order_relaxed);
+        const bool lane = e.algorithm == CLUSTER_FIT &&
+                          (variant == 3 || (variant == 0 && src.nblocks >= (uint64_t)g_lane_min_blocks.load(std::memory_order_relaxed)));
+        if (lane) {
+            // K1 (thread per block, also emits the ordered weighted points) -> K2L (lane per block: search), in chunks
+            for (uint64_t first = 0; first < src.nblocks; first += LANE_CHUNK_BLOCKS) {
+                const uint32_t n = (uint32_t)std::min<uint64_t>(LANE_CHUNK_BLOCKS, src.nblocks - first);
+                const size_t n32 = ((size_t)n + 31) & ~size_t(31);
+                const size_t setup_bytes = n32 * sizeof(uint4), remap_bytes = n32 * sizeof(uint2), pw_bytes = n32 * 16 * sizeof(float4);
+                uint8_t* scratch = nullptr;
+                TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), setup_bytes + remap_bytes + pw_bytes + n32 * sizeof(uint32_t), ctx.pool, st));
+                float4* pw = reinterpret_cast<float4*>(scratch);
+                uint4* setup = reinterpret_cast<uint4*>(scratch + pw_bytes);
+                uint2* remap = reinterpret_cast<uint2*>(scratch + pw_bytes + setup_bytes);
+                uint32_t* perm = reinterpret_cast<uint32_t*>(scratch + pw_bytes + setup_bytes + remap_bytes);
+                const unsigned g1 = (unsigned)((n + SETUP_WINDOW - 1) / SETUP_WINDOW), g2 = (unsigned)((n + LANE_THREADS - 1) / LANE_THREADS);
+                if (format == BC1) cluster_setup_sorted_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pw, perm, first, n);
+                else if (format == BC2) cluster_setup_sorted_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pw, perm, first, n);
+                else cluster_setup_sorted_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pw, perm, first, n);
+                if (format == BC1) cluster_lane_kernel<BC1><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pw, perm, d_out, first, n);
+                else if (format == BC2) cluster_lane_kernel<BC2><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pw, perm, d_out, first, n);
+                else cluster_lane_kernel<BC3><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pw, perm, d_out, first, n);
+                g_launches.fetch_add(2, std::memory_order_relaxed);
+                const cudaError_t launch_err = cudaGetLastError();
+                const cudaError_t free_err = cudaFreeAsync(scratch, st);    // stream-ordered: released after the search kernel
+                if (launch_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit launch: ") + cudaGetErrorString(launch_err));
+                TXP_CUDA(free_err);
+            }
+            return TXP_OK;
+        }
+        if (variant == 1) {                                                                        // single-kernel variant kept for A/B measurements
             if (format == BC1) colour_encode_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
             else if (format == BC2) colour_encode_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
             else colour_encode_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
@@ -358,9 +404,10 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
             uint4* setup = nullptr;
             TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&setup), (size_t)src.nblocks * sizeof(uint4), ctx.pool, st));
             const unsigned g1 = (unsigned)((src.nblocks + 127) / 128);
-            if (format == BC1) cluster_setup_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup);
-            else if (format == BC2) cluster_setup_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup);
-            else cluster_setup_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup);
+            const uint32_t n = (uint32_t)src.nblocks;
+            if (format == BC1) cluster_setup_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, 0, n);
+            else if (format == BC2) cluster_setup_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, 0, n);
+            else cluster_setup_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, 0, n);
             if (format == BC1) colour_search_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
             else if (format == BC2) colour_search_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
             else colour_search_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
@@ -568,7 +615,8 @@ uint64_t txp_kernel_launches(void) { return g_launches.load(); }
 const char* txp_version(void) { return "texpresso_b200 0.1 (sm_100a)"; }
 
 int txp_debug_set(int key, int value) {
-    if (key == 0) { g_colour_fused.store(value ? 1 : 0); return TXP_OK; }
+    if (key == 0) { if (value < 0 || value > 3) return fail(TXP_ERR_ARGUMENT, "colour variant must be 0..3"); g_colour_variant.store(value); return TXP_OK; }
+    if (key == 1) { g_lane_min_blocks.store(value); return TXP_OK; }
     return fail(TXP_ERR_ARGUMENT, "unknown debug key");
 }
 

@@ -1,0 +1,188 @@
+// txp_cluster_lane.cuh -- ClusterFit partition search ("K2L"), one LANE per 4x4 block.
+//
+// Replaces (reference, /root/reference/lib/src): colourfit/cluster.rs:152-274 (compress3), :276-417 (compress4) and the
+// dispatch colourfit.rs:48-59 for Algorithm::ClusterFit (one ordering per pass).  The ordering itself
+// (cluster.rs:78-136) comes from cluster_setup_kernel<FMT, true> as the ordered weighted points.
+//
+// Why a lane per block (measured reasoning in profiles/README.md): the warp-per-block kernel (txp_colour.cuh) spreads the
+// candidates of ONE block over 32 lanes, so every lane evaluates its candidate from scratch out of a range-sum table
+// (3 x LDS.128 + index decoding per candidate), the winner has to be found by a warp reduction and evaluated again
+// (1 of 31 loop trips), the last trip is 7/32 full, and table construction costs every block ~800 warp-instructions.
+// Here every lane walks the reference's own loop nest for its own block:
+//   * part0 / part1 / part2 are running sums exactly as in cluster.rs:303-376 (no table, one LDS.128 per candidate),
+//   * everything that depends on (i, j) only -- part1*(2/3,4/9)+part0 and part1*(1/3,1/9) -- is computed once per (i, j)
+//     instead of once per candidate (same operations, same operands => same bits),
+//   * "first candidate in loop order wins" is the natural strict `<` of a sequential loop, no tie keys,
+//   * the winner is evaluated a second time once per block (1 of 967), to get its endpoints.
+// Lanes of a warp stay converged as long as their blocks have the same number of points, so the setup kernel leaves its
+// a permutation of every window of 1024 blocks sorted by (points, punch-through) (cluster_setup_sorted_kernel).
+#pragma once
+#include "txp_colour.cuh"
+#include "txp_cluster_setup.cuh"
+
+namespace txp {
+
+constexpr int LANE_THREADS = 128;    // one block per thread and CTA: the hardware CTA scheduler balances the load
+#ifndef TXP_LANE_MIN_CTAS
+#define TXP_LANE_MIN_CTAS 6          // 6 CTAs x 4 warps = 24 warps per SM (shared memory: 6 x 34 KB)
+#endif
+
+struct LaneBest { float err; uint32_t key; };          // key: bit 15 = 3-colour pass, i << 10 | j << 5 | k
+constexpr uint32_t LANE_NONE = 0xFFFFFFFFu;
+
+// compress3 (cluster.rs:152-274), one ordering.  col[m * LANE_THREADS] = points_weights[m]; col[count] is a zero guard.
+__device__ __forceinline__ void lane_pass3(const float4* col, const int count, const float4 xsum,
+                                           const EncodeParams& prm, LaneBest& best) {
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int i = 0; i < count; ++i) {
+        // cluster.rs:180-181: part1 starts at points_weights[0] (== 0 + points_weights[0]) with j from 1 when i == 0
+        float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int j = i;
+        if (i == 0) { p1 = col[0]; j = 1; }
+#pragma unroll 1
+        for (; j <= count; ++j) {
+            const float err = eval3_parts(p0, p1, xsum, prm.wx, prm.wy, prm.wz, nullptr, false);
+            if (err < best.err) { best.err = err; best.key = 0x8000u | ((uint32_t)i << 5) | (uint32_t)j; }       // :223 strict
+            p1 = f4add(p1, col[j * LANE_THREADS]);                                    // :233-235 (guard row at j == count)
+        }
+        p0 = f4add(p0, col[i * LANE_THREADS]);                                        // :239
+    }
+}
+
+// compress4 (cluster.rs:276-417), one ordering.
+__device__ __forceinline__ void lane_pass4(const float4* col, const int count, const float4 xsum,
+                                           const EncodeParams& prm, LaneBest& best) {
+    const float c13 = 1.0f / 3.0f, c19 = 1.0f / 9.0f, c23 = 2.0f / 3.0f, c49 = 4.0f / 9.0f, c29 = 2.0f / 9.0f;
+    const f32x2 k13xy = pk(c13, c13), k13zw = pk(c13, c19), k23xy = pk(c23, c23), k23zw = pk(c23, c49);
+    const f32x2 nz = prm.negzero2;
+#ifdef TXP_LANE_LITERAL_GRID
+    const f32x2 gxy = pk(31.0f, 63.0f), grxy = pk(1.0f / 31.0f, 1.0f / 63.0f);
+#else
+    const f32x2 gxy = prm.grid_xy, grxy = prm.gridrcp_xy;        // from the parameter bank: no UMOVs inside the loop
+#endif
+    const f32x2 xs_xy = pk(xsum.x, xsum.y), xs_zw = pk(xsum.z, xsum.w);
+    const f32x2 zero2 = pk(0.f, 0.f);
+    f32x2 p0xy = zero2, p0zw = zero2;
+#pragma unroll 1
+    for (int i = 0; i < count; ++i) {
+        f32x2 p1xy = zero2, p1zw = zero2;
+#pragma unroll 1
+        for (int j = i; j <= count; ++j) {
+            // the (i, j)-only halves of alphax_sum / betax_sum (cluster.rs:323-328)
+            const f32x2 Axy = add2(mul2c(p1xy, k23xy, nz), p0xy), Azw = add2(mul2c(p1zw, k23zw, nz), p0zw);
+            const f32x2 Bxy = mul2c(p1xy, k13xy, nz), Bzw = mul2c(p1zw, k13zw, nz);
+            float p1z_, p1w;
+            upk(p1zw, p1z_, p1w);
+            // cluster.rs:314-315: part2 starts at points_weights[0] with k from 1 when j == 0
+            f32x2 p2xy = zero2, p2zw = zero2;
+            int k0 = j;
+            if (j == 0) { const float4 v = col[0]; p2xy = pk(v.x, v.y); p2zw = pk(v.z, v.w); k0 = 1; }
+            // the loop counter is the candidate's key (i, j, k) itself; next = points_weights[k]
+            const uint32_t ij = ((uint32_t)i << 10) | ((uint32_t)j << 5), key_end = ij | (uint32_t)count;
+            const float4* next = col + k0 * LANE_THREADS;
+#pragma unroll 1
+            for (uint32_t key = ij | (uint32_t)k0; key <= key_end; ++key, next += LANE_THREADS) {
+                const f32x2 p3xy = sub2(sub2(sub2(xs_xy, p2xy), p1xy), p0xy);        // :320
+                const f32x2 p3zw = sub2(sub2(sub2(xs_zw, p2zw), p1zw), p0zw);
+                const f32x2 axy = add2(mul2c(p2xy, k13xy, nz), Axy), azw = add2(mul2c(p2zw, k13zw, nz), Azw);
+                const f32x2 bxy = add2(Bxy, add2(mul2c(p2xy, k23xy, nz), p3xy));
+                const f32x2 bzw = add2(Bzw, add2(mul2c(p2zw, k23zw, nz), p3zw));
+                float az, alpha2, bz, beta2, p2z_, p2w;
+                upk(azw, az, alpha2);
+                upk(bzw, bz, beta2);
+                upk(p2zw, p2z_, p2w);
+                const float ab = mul(c29, add(p1w, p2w));                            // :331
+                const float err = solve_packed(axy, az, alpha2, bxy, bz, beta2, ab, prm.wx, prm.wy, prm.wz, nz, gxy, grxy);
+                if (err < best.err) { best.err = err; best.key = key; }              // :356 strict
+                const float4 v = *next;                                               // :367-369 (guard row at k == count)
+                p2xy = add2(p2xy, pk(v.x, v.y)); p2zw = add2(p2zw, pk(v.z, v.w));
+            }
+            const float4 v = col[j * LANE_THREADS];                                   // :373-375
+            p1xy = add2(p1xy, pk(v.x, v.y)); p1zw = add2(p1zw, pk(v.z, v.w));
+        }
+        const float4 v = col[i * LANE_THREADS];                                       // :379
+        p0xy = add2(p0xy, pk(v.x, v.y)); p0zw = add2(p0zw, pk(v.z, v.w));
+    }
+}
+
+// sum of points_weights[a..b) accumulated from zero, left to right (the value of a running part sum)
+__device__ __forceinline__ float4 lane_range_sum(const float4* col, const int a, const int b) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = a; m < b; ++m) acc = f4add(acc, col[m * LANE_THREADS]);
+    return acc;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_MIN_CTAS) cluster_lane_kernel(const EncodeParams prm,
+                                                                                       const uint4* __restrict__ setup,
+                                                                                       const uint2* __restrict__ remap,
+                                                                                       const float4* __restrict__ pwbuf,
+                                                                                       const uint32_t* __restrict__ perm,
+                                                                                       uint8_t* __restrict__ out,
+                                                                                       const uint64_t first, const uint32_t n) {
+    __shared__ float4 s_pw[17][LANE_THREADS];
+    const int tid = threadIdx.x;
+    const float4* col = &s_pw[0][tid];
+    {
+        // perm is window-sorted by cluster_setup_sorted_kernel: 32 consecutive entries are blocks of (mostly) the same shape
+        const uint32_t slot = blockIdx.x * LANE_THREADS + tid;
+        if (slot >= n) return;
+        const uint32_t lb = __ldg(perm + slot);           // chunk-local block number
+        const uint4 su = __ldg(setup + lb);
+        if (!(su.z & SETUP_SEARCH)) return;               // finished by the setup kernel (0 or 1 points)
+        const int count = (int)(su.z & 31u);
+        for (int m = 0; m < count; ++m) s_pw[m][tid] = __ldg(pwbuf + pw_index(lb, m));
+        s_pw[count][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 xsum = lane_range_sum(col, 0, count);                            // xsum_wsum (cluster.rs:125-133)
+
+        LaneBest best;
+        best.err = FLT_MAX;                                                           // cluster.rs:66
+        best.key = LANE_NONE;
+        if (FMT == BC1) {                                                             // colourfit.rs:48-59
+            lane_pass3(col, count, xsum, prm, best);
+            if (!(su.z & SETUP_TRANSPARENT)) lane_pass4(col, count, xsum, prm, best);
+        } else {
+            lane_pass4(col, count, xsum, prm, best);
+        }
+
+        uint2 block = make_uint2(0u, 0u);                                             // best_compressed starts zeroed (cluster.rs:71)
+        if (best.key != LANE_NONE) {
+            const bool three = (best.key & 0x8000u) != 0;
+            const int bi = (int)((best.key >> (three ? 5 : 10)) & 31u), bj = (int)((best.key >> (three ? 0 : 5)) & 31u);
+            const int bk = three ? bj : (int)(best.key & 31u);     // 3-colour: no third cluster (codes 0, 2, 1)
+            // the winner once more, for its endpoints
+            Solution sol;
+            const float4 p0 = lane_range_sum(col, 0, bi), p1 = lane_range_sum(col, bi, bj);
+            if (three) eval3_parts(p0, p1, xsum, prm.wx, prm.wy, prm.wz, &sol, true);
+            else eval4_parts(p0, p1, lane_range_sum(col, bj, bk), xsum, prm.wx, prm.wy, prm.wz, &sol, true);
+            // unordered[order[m]] = code(m), m ascending (cluster.rs:254-262 / :396-405; later writes win)
+            const unsigned long long ow = (unsigned long long)su.x | ((unsigned long long)su.y << 32);
+            uint32_t pc = 0;                                                          // 2 bits per point
+            for (int m = 0; m < count; ++m) {
+                const uint32_t q = (uint32_t)(ow >> (4 * m)) & 15u;
+                const uint32_t cm = m < bi ? 0u : (m < bj ? 2u : (m < bk ? 3u : 1u));
+                pc = (pc & ~(3u << (2 * q))) | (cm << (2 * q));
+            }
+            // remap_indices (colourset.rs:130-141): pixels without a point get index 3
+            const uint2 rm = __ldg(remap + lb);
+            const uint32_t active16 = su.z >> 16;
+            uint32_t idx2 = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t p = ((i < 8 ? rm.x : rm.y) >> (4 * (i & 7))) & 15u;
+                const uint32_t c = ((active16 >> i) & 1u) ? ((pc >> (2 * p)) & 3u) : 3u;
+                idx2 |= c << (2 * i);
+            }
+            // pack_565 of k*gridrcp is k itself (checked in tests/test_identities.py)
+            const uint32_t a = ((uint32_t)sol.ka[0] << 11) | ((uint32_t)sol.ka[1] << 5) | (uint32_t)sol.ka[2];
+            const uint32_t b = ((uint32_t)sol.kb[0] << 11) | ((uint32_t)sol.kb[1] << 5) | (uint32_t)sol.kb[2];
+            block = three ? write3_packed(a, b, idx2) : write4_packed(a, b, idx2);
+        }
+        uint2* out2 = reinterpret_cast<uint2*>(out);
+        const uint64_t b = first + lb;
+        if (FMT == BC1) out2[b] = block; else out2[2 * b + 1] = block;                // lib.rs:213
+    }
+}
+
+}  // namespace txp

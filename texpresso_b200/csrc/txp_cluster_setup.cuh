@@ -7,7 +7,10 @@
 //     single.rs) and flagged as done
 //   * Sym3x3::weighted_covariance + principle_component (math.rs:44-97)
 //   * construct_ordering for the principal axis (cluster.rs:78-105), which is iteration 0 of compress3 AND compress4
-// The search kernel (txp_colour.cuh) receives 16 bytes per block: the ordering word and flags.
+// The warp-per-block search kernel (txp_colour.cuh) receives 16 bytes per block: the ordering word and flags.
+// With EMIT (lane-per-block search kernel, txp_cluster_lane.cuh) the thread also leaves the ordered weighted points
+// `points_weights` (cluster.rs:126-132) and the pixel -> point remap (colourset.rs:130-141), so that the search kernel
+// never touches the pixels.
 #pragma once
 #include "txp_range.cuh"
 
@@ -16,15 +19,20 @@ namespace txp {
 // setup record: .x/.y = ordering word (4 bits per sorted position: point index, 0 for padding), .z = flags
 constexpr uint32_t SETUP_SEARCH = 0x100u;       // block needs the partition search (>= 2 points)
 constexpr uint32_t SETUP_DEGENERATE = 0x200u;   // some projection is NaN/inf: ordering has repeated entries
+constexpr uint32_t SETUP_TRANSPARENT = 0x400u;  // BC1 punch-through pixels present: no 4-colour pass (colourfit.rs:51)
+// .z bits 0..4 = number of points, bits 16..31 = pixels that belong to a point (valid and not punched through)
 
-template <int FMT>
-__global__ void __launch_bounds__(128) cluster_setup_kernel(const BlockSource src, const EncodeParams prm,
-                                                            uint8_t* __restrict__ out, uint4* __restrict__ setup) {
-    __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = fdiv((float)i, 255.0f);   // colourset.rs:65-67
-    __syncthreads();
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= src.nblocks) return;
+// ordered weighted points of chunk-local block lb, position m: 256 contiguous bytes per block (whole sectors per writer)
+__host__ __device__ __forceinline__ size_t pw_index(const uint32_t lb, const int m) { return (size_t)lb * 16 + m; }
+
+constexpr int SETUP_BINS = 35;                   // sort key: points (2..16) + 17 if punch-through; 34 = no search needed
+
+// One block, chunk-local number lb.  Returns the block's sort key.
+template <int FMT, bool EMIT>
+__device__ __forceinline__ int cluster_setup_block(const BlockSource& src, const EncodeParams& prm, uint8_t* __restrict__ out,
+                                                    uint4* __restrict__ setup, uint2* __restrict__ remap, float4* __restrict__ pwbuf,
+                                                    const float* lut, float4 (*uw)[128], const uint64_t first, const uint32_t lb) {
+    const uint64_t b = first + lb;
     uint32_t px[16];
     uint32_t mask;
     load_block_thread(src, b, px, mask);
@@ -42,13 +50,13 @@ __global__ void __launch_bounds__(128) cluster_setup_kernel(const BlockSource sr
     const ThreadSet ts = thread_colourset<FMT == BC1>(px, mask, prm.alpha_weighted != 0, gw);
     if (ts.active16 == 0) {                              // lib.rs:223 -> RangeFit on an empty set
         *colour_out = FMT == BC1 ? make_uint2(0u, 0xFFFFFFFFu) : make_uint2(0u, 0u);
-        setup[b] = make_uint4(0u, 0u, 0u, 0u);
-        return;
+        setup[lb] = make_uint4(0u, 0u, 0u, 0u);
+        return SETUP_BINS - 1;
     }
     if ((ts.new16 & (ts.new16 - 1u)) == 0u) {            // one point: SingleColourFit (lib.rs:217-222)
         *colour_out = single_fit_thread<FMT == BC1>(thread_single_rgb(px, ts.active16), ts.active16, ts.transparent);
-        setup[b] = make_uint4(0u, 0u, 1u, 0u);
-        return;
+        setup[lb] = make_uint4(0u, 0u, 1u, 0u);
+        return SETUP_BINS - 1;
     }
     float w[16];
     thread_weights(gw, ts.new16, prm.alpha_weighted != 0, w);
@@ -90,7 +98,92 @@ __global__ void __launch_bounds__(128) cluster_setup_kernel(const BlockSource sr
             if (rank[i] < 8) lo |= p << (4 * rank[i]); else hi |= p << (4 * (rank[i] - 8));
         }
     }
-    setup[b] = make_uint4(lo, hi, (uint32_t)__popc(ts.new16) | SETUP_SEARCH | (degenerate ? SETUP_DEGENERATE : 0u), 0u);
+    const int count = __popc(ts.new16);
+    setup[lb] = make_uint4(lo, hi, (uint32_t)count | SETUP_SEARCH | (degenerate ? SETUP_DEGENERATE : 0u) |
+                                   (ts.transparent ? SETUP_TRANSPARENT : 0u) | (ts.active16 << 16), 0u);
+    if (EMIT) {
+        // pixel -> point (colourset.rs:84-88): the point of the first pixel with the same key
+        uint32_t rlo = 0, rhi = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int f = i;
+#pragma unroll
+            for (int j = i - 1; j >= 0; --j) if (px[j] == px[i]) f = j;
+            const uint32_t p = (uint32_t)__popc(ts.new16 & ((1u << f) - 1u));
+            if (i < 8) rlo |= p << (4 * i); else rhi |= p << (4 * (i - 8));
+        }
+        remap[lb] = make_uint2(rlo, rhi);
+        // weighted points (cluster.rs:126-129: (x, y, z, 1) * w) in set order, then in the order of the principal axis
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if ((ts.new16 >> i) & 1u) {
+                const float x = lut[px[i] & 255u], y = lut[(px[i] >> 8) & 255u], z = lut[(px[i] >> 16) & 255u];
+                uw[p][threadIdx.x] = make_float4(mul(x, w[i]), mul(y, w[i]), mul(z, w[i]), w[i]);
+                ++p;
+            }
+        }
+        const unsigned long long ow = (unsigned long long)lo | ((unsigned long long)hi << 32);
+        for (int m = 0; m < count; ++m) pwbuf[pw_index(lb, m)] = uw[(ow >> (4 * m)) & 15ull][threadIdx.x];
+    }
+    return count + (ts.transparent ? 17 : 0);
+}
+
+// Blocks [first, first + n) of `src`; the records are indexed by the chunk-local block number.
+template <int FMT>
+__global__ void __launch_bounds__(128) cluster_setup_kernel(const BlockSource src, const EncodeParams prm,
+                                                            uint8_t* __restrict__ out, uint4* __restrict__ setup,
+                                                            const uint64_t first, const uint32_t n) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = fdiv((float)i, 255.0f);   // colourset.rs:65-67
+    __syncthreads();
+    const uint32_t lb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lb >= n) return;
+    cluster_setup_block<FMT, false>(src, prm, out, setup, nullptr, nullptr, lut, nullptr, first, lb);
+}
+
+// Setup for the lane-per-block search kernel.  One CTA owns a window of SETUP_WINDOW consecutive blocks (one block per
+// thread and round) and also leaves the window's permutation sorted by (points, punch-through), blocks that need no
+// search last: perm[s] = chunk-local block number of the s-th record in sorted order.  The 32 lanes of a search warp take
+// 32 consecutive entries of perm, i.e. (mostly) blocks whose loop nests have the same shape.
+constexpr int SETUP_WINDOW_ROUNDS = 8;
+constexpr int SETUP_WINDOW = 128 * SETUP_WINDOW_ROUNDS;
+
+template <int FMT>
+__global__ void __launch_bounds__(128) cluster_setup_sorted_kernel(const BlockSource src, const EncodeParams prm,
+                                                                   uint8_t* __restrict__ out, uint4* __restrict__ setup,
+                                                                   uint2* __restrict__ remap, float4* __restrict__ pwbuf,
+                                                                   uint32_t* __restrict__ perm, const uint64_t first, const uint32_t n) {
+    __shared__ float lut[256];
+    __shared__ float4 uw[16][128];                        // weighted points in set order, one column per thread
+    __shared__ int hist[SETUP_BINS];
+    __shared__ uint16_t s_rank[SETUP_WINDOW];
+    __shared__ uint8_t s_key[SETUP_WINDOW];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += 128) lut[i] = fdiv((float)i, 255.0f);                  // colourset.rs:65-67
+    if (tid < SETUP_BINS) hist[tid] = 0;
+    __syncthreads();
+    const uint32_t win0 = blockIdx.x * SETUP_WINDOW;
+#pragma unroll 1
+    for (int r = 0; r < SETUP_WINDOW_ROUNDS; ++r) {
+        const uint32_t lb = win0 + r * 128 + tid;
+        if (lb >= n) break;
+        const int key = cluster_setup_block<FMT, true>(src, prm, out, setup, remap, pwbuf, lut, uw, first, lb);
+        s_key[r * 128 + tid] = (uint8_t)key;
+        s_rank[r * 128 + tid] = (uint16_t)atomicAdd(&hist[key], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < SETUP_BINS; ++k) { const int c = hist[k]; hist[k] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < SETUP_WINDOW_ROUNDS; ++r) {
+        const uint32_t lb = win0 + r * 128 + tid;
+        if (lb >= n) break;
+        perm[win0 + (uint32_t)hist[s_key[r * 128 + tid]] + s_rank[r * 128 + tid]] = lb;
+    }
 }
 
 }  // namespace txp

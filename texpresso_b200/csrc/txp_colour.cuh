@@ -93,10 +93,9 @@ __device__ __forceinline__ float solve(const float4 alphax, const float4 betax, 
     return add(add(e5[0], e5[1]), e5[2]);
 }
 
-__device__ __forceinline__ float eval3(const float4* S, const uint32_t E, const float4 xsum,
-                                       const float wx, const float wy, const float wz, Solution* out, bool want) {
-    const float4 p0 = S[E >> 9];                 // S[0][i]
-    const float4 p1 = S[E & 511u];               // S[i][j]
+// One 3-colour candidate from its cluster sums: p0 = part0, p1 = part1 (cluster.rs:189-220).
+__device__ __forceinline__ float eval3_parts(const float4 p0, const float4 p1, const float4 xsum,
+                                             const float wx, const float wy, const float wz, Solution* out, bool want) {
     const float4 p2 = f4sub(f4sub(xsum, p1), p0);                                   // cluster.rs:189
     const float4 p1h = make_float4(mul(p1.x, 0.5f), mul(p1.y, 0.5f), mul(p1.z, 0.5f), mul(p1.w, 0.25f));
     const float4 alphax = f4add(p1h, p0);                                            // :192
@@ -104,12 +103,15 @@ __device__ __forceinline__ float eval3(const float4* S, const uint32_t E, const 
     return want ? solve<true>(alphax, betax, p1h.w, wx, wy, wz, out) : solve<false>(alphax, betax, p1h.w, wx, wy, wz, out);
 }
 
-__device__ __forceinline__ float eval4(const float4* S, const uint32_t E, const float4 xsum,
+__device__ __forceinline__ float eval3(const float4* S, const uint32_t E, const float4 xsum,
                                        const float wx, const float wy, const float wz, Solution* out, bool want) {
+    return eval3_parts(S[E >> 9] /* S[0][i] */, S[E & 511u] /* S[i][j] */, xsum, wx, wy, wz, out, want);
+}
+
+// One 4-colour candidate from its cluster sums p0, p1, p2 = part0, part1, part2 (cluster.rs:320-353).
+__device__ __forceinline__ float eval4_parts(const float4 p0, const float4 p1, const float4 p2, const float4 xsum,
+                                             const float wx, const float wy, const float wz, Solution* out, bool want) {
     const float c13 = 1.0f / 3.0f, c19 = 1.0f / 9.0f, c23 = 2.0f / 3.0f, c49 = 4.0f / 9.0f, c29 = 2.0f / 9.0f;
-    const float4 p0 = S[E >> 18];                // S[0][i]
-    const float4 p1 = S[(E >> 9) & 511u];        // S[i][j]
-    const float4 p2 = S[E & 511u];               // S[j][k]
     const float4 p3 = f4sub(f4sub(f4sub(xsum, p2), p1), p0);                         // cluster.rs:320
     float4 alphax, betax;                                                            // :323-328
     alphax.x = add(mul(p2.x, c13), add(mul(p1.x, c23), p0.x));
@@ -122,6 +124,50 @@ __device__ __forceinline__ float eval4(const float4* S, const uint32_t E, const 
     betax.w = add(mul(p1.w, c19), add(mul(p2.w, c49), p3.w));
     const float ab = mul(c29, add(p1.w, p2.w));                                      // :331
     return want ? solve<true>(alphax, betax, ab, wx, wy, wz, out) : solve<false>(alphax, betax, ab, wx, wy, wz, out);
+}
+
+__device__ __forceinline__ float eval4(const float4* S, const uint32_t E, const float4 xsum,
+                                       const float wx, const float wy, const float wz, Solution* out, bool want) {
+    return eval4_parts(S[E >> 18] /* S[0][i] */, S[(E >> 9) & 511u] /* S[i][j] */, S[E & 511u] /* S[j][k] */, xsum, wx, wy, wz, out, want);
+}
+
+// Second half of a 4-colour candidate with the x/y lanes carried as fp32x2 pairs: endpoints, grid snap and error
+// (cluster.rs:334-353) from alphax = (axy, az, alpha2), betax = (bxy, bz, beta2) and ab = alphabeta_sum.
+__device__ __forceinline__ float solve_packed(const f32x2 axy, const float az, const float alpha2, const f32x2 bxy, const float bz,
+                                              const float beta2, const float ab, const float wx, const float wy, const float wz,
+                                              const f32x2 nz, const f32x2 gxy, const f32x2 grxy) {
+    const float factor = rcp_normal(sub(mul(alpha2, beta2), mul(ab, ab)));           // :334-335
+    float nax, nay, nbx, nby;                                                        // :336-337
+    upk(sub2(mul2s(axy, beta2), mul2s(bxy, ab)), nax, nay);
+    upk(sub2(mul2s(bxy, alpha2), mul2s(axy, ab)), nbx, nby);
+    const float cax = clamp01(mul(nax, factor)), cay = clamp01(mul(nay, factor));    // :340-341
+    const float cbx = clamp01(mul(nbx, factor)), cby = clamp01(mul(nby, factor));
+    const float caz = clamp01(mul(sub(mul(az, beta2), mul(bz, ab)), factor));
+    const float cbz = clamp01(mul(sub(mul(bz, alpha2), mul(az, ab)), factor));
+    // grid snap :342-343  (x,y) pairs use (31,63); the z values of a and b share one pair
+    const f32x2 hh = pk(0.5f, 0.5f);
+    const f32x2 g31 = pk(31.0f, 31.0f), gr31 = pk(1.0f / 31.0f, 1.0f / 31.0f);
+    float t0, t1;
+    upk(add2(mul2c(pk(cax, cay), gxy, nz), hh), t0, t1);
+    const f32x2 a2 = mul2m(pk(truncf(t0), truncf(t1)), grxy);                        // feeds multiplies only
+    upk(add2(mul2c(pk(cbx, cby), gxy, nz), hh), t0, t1);
+    const f32x2 b2 = mul2m(pk(truncf(t0), truncf(t1)), grxy);
+    upk(add2(mul2c(pk(caz, cbz), g31, nz), hh), t0, t1);
+    float qaz, qbz;
+    upk(mul2m(pk(truncf(t0), truncf(t1)), gr31), qaz, qbz);
+    // error terms :346-353, x/y packed
+    const f32x2 e1 = add2(mul2s(mul2m(a2, a2), alpha2), mul2s(mul2m(b2, b2), beta2));
+    const f32x2 e2 = sub2(mul2s(mul2m(a2, b2), ab), mul2s(a2, axy));
+    const f32x2 e3 = sub2(e2, mul2s(b2, bxy));
+    const f32x2 e4 = fma2(pk(2.0f, 2.0f), e3, e1);        // 2*e3 exact -> same as (2*e3)+e1
+    float e5x, e5y;
+    upk(mul2c(e4, pk(wx, wy), nz), e5x, e5y);
+    // z scalar
+    const float e1z = add(mul(mul(qaz, qaz), alpha2), mul(mul(qbz, qbz), beta2));
+    const float e2z = sub(mul(mul(qaz, qbz), ab), mul(qaz, az));
+    const float e3z = sub(e2z, mul(qbz, bz));
+    const float e5z = mul(__fmaf_rn(2.0f, e3z, e1z), wz);
+    return add(add(e5x, e5y), e5z);
 }
 
 // eval4 with the x/y lanes (and the z/w lanes of the sums) carried as fp32x2 pairs.  Same operations, same
@@ -146,38 +192,7 @@ __device__ __forceinline__ float eval4_packed(const float4* S, const uint32_t E,
     upk(azw, az, alpha2);
     upk(bzw, bz, beta2);
     const float ab = mul(c29, add(p1.w, p2.w));                                      // :331
-    const float factor = rcp_normal(sub(mul(alpha2, beta2), mul(ab, ab)));           // :334-335
-    float nax, nay, nbx, nby;                                                        // :336-337
-    upk(sub2(mul2s(axy, beta2), mul2s(bxy, ab)), nax, nay);
-    upk(sub2(mul2s(bxy, alpha2), mul2s(axy, ab)), nbx, nby);
-    const float cax = clamp01(mul(nax, factor)), cay = clamp01(mul(nay, factor));    // :340-341
-    const float cbx = clamp01(mul(nbx, factor)), cby = clamp01(mul(nby, factor));
-    const float caz = clamp01(mul(sub(mul(az, beta2), mul(bz, ab)), factor));
-    const float cbz = clamp01(mul(sub(mul(bz, alpha2), mul(az, ab)), factor));
-    // grid snap :342-343  (x,y) pairs use (31,63); the z values of a and b share one pair
-    const f32x2 gxy = pk(31.0f, 63.0f), grxy = pk(1.0f / 31.0f, 1.0f / 63.0f), hh = pk(0.5f, 0.5f);
-    const f32x2 g31 = pk(31.0f, 31.0f), gr31 = pk(1.0f / 31.0f, 1.0f / 31.0f);
-    float t0, t1;
-    upk(add2(mul2c(pk(cax, cay), gxy, nz), hh), t0, t1);
-    const f32x2 a2 = mul2m(pk(truncf(t0), truncf(t1)), grxy);                        // feeds multiplies only
-    upk(add2(mul2c(pk(cbx, cby), gxy, nz), hh), t0, t1);
-    const f32x2 b2 = mul2m(pk(truncf(t0), truncf(t1)), grxy);
-    upk(add2(mul2c(pk(caz, cbz), g31, nz), hh), t0, t1);
-    float qaz, qbz;
-    upk(mul2m(pk(truncf(t0), truncf(t1)), gr31), qaz, qbz);
-    // error terms :346-353, x/y packed
-    const f32x2 e1 = add2(mul2s(mul2m(a2, a2), alpha2), mul2s(mul2m(b2, b2), beta2));
-    const f32x2 e2 = sub2(mul2s(mul2m(a2, b2), ab), mul2s(a2, axy));
-    const f32x2 e3 = sub2(e2, mul2s(b2, bxy));
-    const f32x2 e4 = fma2(pk(2.0f, 2.0f), e3, e1);        // 2*e3 exact -> same as (2*e3)+e1
-    float e5x, e5y;
-    upk(mul2c(e4, pk(wx, wy), nz), e5x, e5y);
-    // z scalar
-    const float e1z = add(mul(mul(qaz, qaz), alpha2), mul(mul(qbz, qbz), beta2));
-    const float e2z = sub(mul(mul(qaz, qbz), ab), mul(qaz, az));
-    const float e3z = sub(e2z, mul(qbz, bz));
-    const float e5z = mul(__fmaf_rn(2.0f, e3z, e1z), wz);
-    return add(add(e5x, e5y), e5z);
+    return solve_packed(axy, az, alpha2, bxy, bz, beta2, ab, wx, wy, wz, nz, pk(31.0f, 63.0f), pk(1.0f / 31.0f, 1.0f / 63.0f));
 }
 
 // The per-block state every fit needs.

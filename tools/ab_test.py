@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Interleaved A/B timing of ClusterFit kernel variants in ONE process (cancels clock / thermal drift).
-usage: ab_test.py name=lib.so[:fused] ...   (each variant = a built library, optionally the fused kernel)"""
+usage: ab_test.py name=lib.so[:auto|fused|warp|lane] ...   (each variant = a built library + a ClusterFit kernel structure)"""
 import ctypes, json, pathlib, statistics, subprocess, sys, threading
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -9,15 +9,18 @@ import texpresso_b200 as T
 from texpresso_b200 import synth, _lib
 
 variants = []
-for a in sys.argv[1:]:
+only = None
+args = sys.argv[1:]
+if args and args[0].startswith("--cases="):
+    only = args.pop(0).split("=", 1)[1].split(",")
+for a in args:
     name, spec = a.split("=")
     path, _, mode = spec.partition(":")
     L = ctypes.CDLL(str(pathlib.Path(path).resolve()))
     L.txp_compress_device.restype = ctypes.c_int
     L.txp_compress_device.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(_lib.CParams), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.txp_debug_set.argtypes = [ctypes.c_int, ctypes.c_int]
-    L.txp_debug_set(0, 1 if mode == "fused" else 0)
-    variants.append((name, L))
+    variants.append((name, L, {"": 0, "auto": 0, "fused": 1, "warp": 2, "lane": 3}[mode]))
 
 torch.cuda.set_device(0)
 w = h = 8192
@@ -29,7 +32,9 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 cases = [("bc3", 2, d3, 16, T.Params()), ("bc1", 0, d1, 8, T.Params()),
          ("bc1_iter", 0, d1, 8, T.Params(T.Algorithm.IterativeClusterFit)), ("bc3_smooth", 2, sm, 16, T.Params()),
-         ("bc3_smooth_iter", 2, sm, 16, T.Params(T.Algorithm.IterativeClusterFit))]
+         ("bc3_smooth_iter", 2, sm, 16, T.Params(T.Algorithm.IterativeClusterFit)), ("bc1_smooth", 0, sm, 8, T.Params())]
+if only:
+    cases = [c for c in cases if c[0] in only]
 clk = []
 p = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
 threading.Thread(target=lambda: [clk.append(l) for l in p.stdout], daemon=True).start()
@@ -37,9 +42,10 @@ res = {}
 for cname, fmt, d, bs, prm in cases:
     out = torch.empty((w // 4) * (h // 4) * bs, dtype=torch.uint8, device="cuda")
     cp = prm._c()
-    times = {n: [] for n, _ in variants}
+    times = {n: [] for n, _, _ in variants}
     for rep in range(6):
-        for n, L in variants:
+        for n, L, mode in variants:
+            L.txp_debug_set(0, mode)            # per call: two variants may share one library (same globals)
             flush.fill_(rep)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
