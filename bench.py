@@ -10,8 +10,9 @@ lib.rs:300-305), every rank encodes its own slice, no collective on the data pat
 
 value  : whole-job Mpix/s, inputs resident in HBM, device time (CUDA events on the launching stream), max over ranks
 e2e    : same metric through the public host API (Format.compress on pinned host buffers: H2D + kernels + D2H)
-roofline : dominant kernel (colour_encode_kernel<BC3>), algorithmic fp32 ops / event time vs the non-FMA
-           FP32 issue peak (SMs x 128 lanes x clock).  Not a tensor/HBM kernel: see DESIGN.md.
+roofline : dominant kernels (cluster_setup_sorted_kernel<BC3> + cluster_lane_kernel<BC3>, one BC3 ClusterFit launch pair),
+           algorithmic fp32 ops / event time vs the non-FMA FP32 issue peak (SMs x 128 lanes x clock).
+           Not a tensor/HBM kernel: see DESIGN.md.
 cpu_baseline : the CPU oracle (a C port of the reference algorithm; the Rust reference cannot be built
            in this image) on all host cores, on a bounded crop of the same workload.
 """
@@ -287,13 +288,14 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps, "api": "Format.compress(pinned host rgba) -> pinned host blocks"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "colour_encode_kernel<BC3> (ClusterFit, 16 colours/block)", "bound": "fp32_issue",
+            "roofline": {"kernel": "cluster_setup_sorted_kernel<BC3> + cluster_lane_kernel<BC3> (ClusterFit, 16 colours/block)", "bound": "fp32_issue",
                          "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": f"derived: {props.multi_processor_count} SMs x 128 lanes x {sm_max:.0f} MHz (MEASURED_PEAKS sm_max_mhz), 1 flop per lane-instruction (no FMA contraction allowed)",
                          "flops_per_block": FLOPS_BC3,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one 8192^2 launch (ncu --set full,
-                         # profiles/ncu_colour_r01_summary.json: 272.3 MB + 53.2 MB; algorithmic 268.4 + 67.1 MB), scaled to this rank's blocks
-                         "traffic": int(325.49e6 * blocks_rank / 4194304),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one 8192^2 launch pair (ncu --set full,
+                         # profiles/ncu_lane_r01_summary.txt: setup 335.7 MB + 1204 MB, search 1254 MB + 65.3 MB; algorithmic
+                         # 268.4 + 67.1 MB -- the rest is the 284 B/block scratch between the two kernels), scaled to this rank's blocks
+                         "traffic": int(2859.4e6 * blocks_rank / 4194304),
                          "hbm_context": {"achieved_gbs": bc3_gbs, "peak_gbs": hbm_peak, "frac": bc3_gbs / hbm_peak}},
             "paths_agree": same,
         }

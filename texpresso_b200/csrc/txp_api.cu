@@ -145,7 +145,7 @@ static std::atomic<int> g_colour_variant{[] {
     const std::string s = v ? v : "";
     return s == "fused" ? 1 : s == "warp" ? 2 : s == "lane" ? 3 : 0;
 }()};
-static std::atomic<long long> g_lane_min_blocks{[] { const char* v = getenv("TXP_LANE_MIN_BLOCKS"); return v ? atoll(v) : 131072ll; }()};
+static std::atomic<long long> g_lane_min_blocks{[] { const char* v = getenv("TXP_LANE_MIN_BLOCKS"); return v ? atoll(v) : 262144ll; }()};
 constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (284 B of scratch per block)
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }

@@ -23,6 +23,9 @@
 namespace txp {
 
 constexpr int LANE_THREADS = 128;    // one block per thread and CTA: the hardware CTA scheduler balances the load
+#ifndef TXP_LANE_UNROLL
+#define TXP_LANE_UNROLL 1            // candidates per trip of the k loop
+#endif
 #ifndef TXP_LANE_MIN_CTAS
 #define TXP_LANE_MIN_CTAS 6          // 6 CTAs x 4 warps = 24 warps per SM (shared memory: 6 x 34 KB)
 #endif
@@ -54,12 +57,21 @@ __device__ __forceinline__ void lane_pass3(const float4* col, const int count, c
 __device__ __forceinline__ void lane_pass4(const float4* col, const int count, const float4 xsum,
                                            const EncodeParams& prm, LaneBest& best) {
     const float c13 = 1.0f / 3.0f, c19 = 1.0f / 9.0f, c23 = 2.0f / 3.0f, c49 = 4.0f / 9.0f, c29 = 2.0f / 9.0f;
-    const f32x2 k13xy = pk(c13, c13), k13zw = pk(c13, c19), k23xy = pk(c23, c23), k23zw = pk(c23, c49);
+    const f32x2 k13xy = pk(c13, c13), k23xy = pk(c23, c23);
     const f32x2 nz = prm.negzero2;
 #ifdef TXP_LANE_LITERAL_GRID
     const f32x2 gxy = pk(31.0f, 63.0f), grxy = pk(1.0f / 31.0f, 1.0f / 63.0f);
 #else
     const f32x2 gxy = prm.grid_xy, grxy = prm.gridrcp_xy;        // from the parameter bank: no UMOVs inside the loop
+#endif
+    // z/w products with the lane-asymmetric multipliers (1/3, 1/9) and (2/3, 4/9) as two scalar FMULs with immediates: as
+    // an FFMA2 they would read three distinct vector register pairs (2/3 rate, profiles/README.md)
+#ifdef TXP_LANE_ZW_PACKED
+#define TXP_ZW13(v) mul2c(v, pk(c13, c19), nz)
+#define TXP_ZW23(v) mul2c(v, pk(c23, c49), nz)
+#else
+#define TXP_ZW13(v) mul2s(v, pk(c13, c19))
+#define TXP_ZW23(v) mul2s(v, pk(c23, c49))
 #endif
     const f32x2 xs_xy = pk(xsum.x, xsum.y), xs_zw = pk(xsum.z, xsum.w);
     const f32x2 zero2 = pk(0.f, 0.f);
@@ -70,8 +82,8 @@ __device__ __forceinline__ void lane_pass4(const float4* col, const int count, c
 #pragma unroll 1
         for (int j = i; j <= count; ++j) {
             // the (i, j)-only halves of alphax_sum / betax_sum (cluster.rs:323-328)
-            const f32x2 Axy = add2(mul2c(p1xy, k23xy, nz), p0xy), Azw = add2(mul2c(p1zw, k23zw, nz), p0zw);
-            const f32x2 Bxy = mul2c(p1xy, k13xy, nz), Bzw = mul2c(p1zw, k13zw, nz);
+            const f32x2 Axy = add2(mul2c(p1xy, k23xy, nz), p0xy), Azw = add2(TXP_ZW23(p1zw), p0zw);
+            const f32x2 Bxy = mul2c(p1xy, k13xy, nz), Bzw = TXP_ZW13(p1zw);
             float p1z_, p1w;
             upk(p1zw, p1z_, p1w);
             // cluster.rs:314-315: part2 starts at points_weights[0] with k from 1 when j == 0
@@ -81,19 +93,40 @@ __device__ __forceinline__ void lane_pass4(const float4* col, const int count, c
             // the loop counter is the candidate's key (i, j, k) itself; next = points_weights[k]
             const uint32_t ij = ((uint32_t)i << 10) | ((uint32_t)j << 5), key_end = ij | (uint32_t)count;
             const float4* next = col + k0 * LANE_THREADS;
-#pragma unroll 1
+TXP_UNROLL(TXP_LANE_UNROLL)
             for (uint32_t key = ij | (uint32_t)k0; key <= key_end; ++key, next += LANE_THREADS) {
+#if defined(TXP_LANE_SCALAR_ALL) || defined(TXP_LANE_SCALAR_SUMS)
+                // A/B variants: the sums (and with _ALL the whole candidate) as scalar operations
+                float s0x, s0y, s0z, s0w, s1x, s1y, s1z, s1w, s2x, s2y, s2z, s2w, Ax, Ay, Az, Aw, Bx, By, Bz, Bw;
+                upk(p0xy, s0x, s0y); upk(p0zw, s0z, s0w); upk(p1xy, s1x, s1y); upk(p1zw, s1z, s1w);
+                upk(p2xy, s2x, s2y); upk(p2zw, s2z, s2w); upk(Axy, Ax, Ay); upk(Azw, Az, Aw); upk(Bxy, Bx, By); upk(Bzw, Bz, Bw);
+                const float p3x = sub(sub(sub(xsum.x, s2x), s1x), s0x), p3y = sub(sub(sub(xsum.y, s2y), s1y), s0y);
+                const float p3z = sub(sub(sub(xsum.z, s2z), s1z), s0z), p3w = sub(sub(sub(xsum.w, s2w), s1w), s0w);
+                float4 alphax, betax;
+                alphax.x = add(mul(s2x, c13), Ax); alphax.y = add(mul(s2y, c13), Ay);
+                alphax.z = add(mul(s2z, c13), Az); alphax.w = add(mul(s2w, c19), Aw);
+                betax.x = add(Bx, add(mul(s2x, c23), p3x)); betax.y = add(By, add(mul(s2y, c23), p3y));
+                betax.z = add(Bz, add(mul(s2z, c23), p3z)); betax.w = add(Bw, add(mul(s2w, c49), p3w));
+                const float ab = mul(c29, add(s1w, s2w));
+#ifdef TXP_LANE_SCALAR_ALL
+                const float err = solve<false>(alphax, betax, ab, prm.wx, prm.wy, prm.wz, nullptr);
+#else
+                const float err = solve_packed(pk(alphax.x, alphax.y), alphax.z, alphax.w, pk(betax.x, betax.y), betax.z, betax.w, ab,
+                                               prm.wx, prm.wy, prm.wz, nz, gxy, grxy);
+#endif
+#else
                 const f32x2 p3xy = sub2(sub2(sub2(xs_xy, p2xy), p1xy), p0xy);        // :320
                 const f32x2 p3zw = sub2(sub2(sub2(xs_zw, p2zw), p1zw), p0zw);
-                const f32x2 axy = add2(mul2c(p2xy, k13xy, nz), Axy), azw = add2(mul2c(p2zw, k13zw, nz), Azw);
+                const f32x2 axy = add2(mul2c(p2xy, k13xy, nz), Axy), azw = add2(TXP_ZW13(p2zw), Azw);
                 const f32x2 bxy = add2(Bxy, add2(mul2c(p2xy, k23xy, nz), p3xy));
-                const f32x2 bzw = add2(Bzw, add2(mul2c(p2zw, k23zw, nz), p3zw));
+                const f32x2 bzw = add2(Bzw, add2(TXP_ZW23(p2zw), p3zw));
                 float az, alpha2, bz, beta2, p2z_, p2w;
                 upk(azw, az, alpha2);
                 upk(bzw, bz, beta2);
                 upk(p2zw, p2z_, p2w);
                 const float ab = mul(c29, add(p1w, p2w));                            // :331
                 const float err = solve_packed(axy, az, alpha2, bxy, bz, beta2, ab, prm.wx, prm.wy, prm.wz, nz, gxy, grxy);
+#endif
                 if (err < best.err) { best.err = err; best.key = key; }              // :356 strict
                 const float4 v = *next;                                               // :367-369 (guard row at k == count)
                 p2xy = add2(p2xy, pk(v.x, v.y)); p2zw = add2(p2zw, pk(v.z, v.w));
@@ -104,6 +137,8 @@ __device__ __forceinline__ void lane_pass4(const float4* col, const int count, c
         const float4 v = col[i * LANE_THREADS];                                       // :379
         p0xy = add2(p0xy, pk(v.x, v.y)); p0zw = add2(p0zw, pk(v.z, v.w));
     }
+#undef TXP_ZW13
+#undef TXP_ZW23
 }
 
 // sum of points_weights[a..b) accumulated from zero, left to right (the value of a running part sum)
