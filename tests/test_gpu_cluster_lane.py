@@ -1,6 +1,6 @@
-"""GPU parity tests for the lane-per-block ClusterFit search kernel (texpresso_b200/csrc/txp_cluster_lane.cuh).
+"""GPU parity tests for the lane-per-block ClusterFit / IterativeClusterFit search kernels (texpresso_b200/csrc/txp_cluster_lane.cuh).
 
-In automatic mode that kernel is only taken by launches of >= 131072 blocks, so these tests force it
+In automatic mode those kernels are only taken by launches of >= 262144 blocks, so these tests force them
 (txp_debug_set(0, 3)) on the small corpora the oracle finishes quickly: every dispatch class and edge case of
 tests/blockgen.py, the random fuzz corpus, ragged images (edge masks), a smooth image (tiles with mixed point counts:
 exercises the per-tile counting sort) and a mip chain.  Bit-exact, and identical to the warp-per-block kernel."""
@@ -32,68 +32,86 @@ def _set_variant(v):
 
 @pytest.mark.parametrize("awa", [False, True])
 @pytest.mark.parametrize("wname", ["uniform", "perceptual", "odd"])
+@pytest.mark.parametrize("alg", [1, 2])
 @pytest.mark.parametrize("fmt", [0, 1, 2])
-def test_lane_clusterfit_blocks_bit_exact(TL, fmt, wname, awa):
+def test_lane_clusterfit_blocks_bit_exact(TL, fmt, alg, wname, awa):
     T = TL
     blocks, masks, tags = blockgen.colour_cases()
-    tp = T.Params(T.Algorithm(1), tuple(WEIGHTS[wname]), awa)
+    tp = T.Params(T.Algorithm(alg), tuple(WEIGHTS[wname]), awa)
     got = T.compress_blocks(fmt, blocks, masks, tp)
-    want = O.compress_blocks(fmt, blocks, masks, O.make_params(1, WEIGHTS[wname], awa))
+    want = O.compress_blocks(fmt, blocks, masks, O.make_params(alg, WEIGHTS[wname], awa))
     diff = np.nonzero((got != want).any(axis=1))[0]
     assert diff.size == 0, (diff.size, [(int(i), tags[i], hex(int(masks[i])), bytes(got[i]).hex(), bytes(want[i]).hex()) for i in diff[:6]])
 
 
+@pytest.mark.parametrize("alg", [1, 2])
 @pytest.mark.parametrize("fmt,weights,awa", [(0, O.PERCEPTUAL, False), (0, O.UNIFORM, True), (1, O.PERCEPTUAL, False), (2, O.PERCEPTUAL, True)])
-def test_lane_random_blocks_bit_exact(TL, fmt, weights, awa):
+def test_lane_random_blocks_bit_exact(TL, fmt, weights, awa, alg):
     T = TL
-    blocks, masks = _corpus(7000 + fmt)
-    tp = T.Params(T.Algorithm(1), tuple(weights), awa)
+    blocks, masks = _corpus(7000 + fmt + 100 * alg)
+    tp = T.Params(T.Algorithm(alg), tuple(weights), awa)
     got = T.compress_blocks(fmt, blocks, masks, tp)
-    want = O.compress_blocks(fmt, blocks, masks, O.make_params(1, weights, awa))
+    want = O.compress_blocks(fmt, blocks, masks, O.make_params(alg, weights, awa))
     diff = np.nonzero((got != want).any(axis=1))[0]
     assert diff.size == 0, (diff.size, [(int(i), hex(int(masks[i])), bytes(blocks[i].reshape(-1)).hex(), bytes(got[i]).hex(), bytes(want[i]).hex()) for i in diff[:3]])
 
 
 @pytest.mark.parametrize("kind,w,h", [("smooth", 260, 131), ("noise_alpha", 129, 67), ("smooth", 1024, 512), ("noise_opaque", 5, 3)])
+@pytest.mark.parametrize("alg", [1, 2])
 @pytest.mark.parametrize("fmt", [0, 1, 2])
-def test_lane_images_bit_exact(TL, fmt, kind, w, h):
+def test_lane_images_bit_exact(TL, fmt, alg, kind, w, h):
     T = TL
     from texpresso_b200 import synth
     img = synth.generate(kind, w, h, seed=11)
-    tp = T.Params(T.Algorithm(1), tuple(O.PERCEPTUAL), False)
+    tp = T.Params(T.Algorithm(alg), tuple(O.PERCEPTUAL), False)
     got = T.Format(fmt).compress(img, w, h, tp)
-    want = O.compress(fmt, img, w, h, O.make_params(1, O.PERCEPTUAL, False), threads=8)
+    want = O.compress(fmt, img, w, h, O.make_params(alg, O.PERCEPTUAL, False), threads=8)
     bs = 8 if fmt == 0 else 16
     nd = int((got.reshape(-1, bs) != want.reshape(-1, bs)).any(axis=1).sum())
     assert nd == 0, (fmt, kind, nd)
 
 
 def test_lane_equals_warp_kernel_and_auto_threshold():
-    """The three kernel structures give the same bytes; automatic mode switches at the block-count threshold."""
+    """The kernel structures give the same bytes on a single device-resident launch of 262144 blocks (the automatic
+    threshold), and automatic mode takes the lane kernels there (one more launch per call than the warp structure for BC1
+    IterativeClusterFit: setup + compress3 + compress4)."""
+    import ctypes
+    import torch
     import texpresso_b200 as T
     from texpresso_b200 import synth, _lib
     L = _lib.load()
-    w, h = 2048, 1024                                # 131072 blocks: the automatic threshold
+    w = h = 2048
     for kind in ("smooth", "noise_alpha"):
         img = synth.generate(kind, w, h, seed=21)
-        for fmt in (0, 2):
-            outs = {}
+        d = torch.from_numpy(img.reshape(-1)).cuda()
+        for fmt, alg in ((0, 1), (2, 1), (0, 2), (1, 2)):
+            bs = 8 if fmt == 0 else 16
+            cp = T.Params(T.Algorithm(alg))._c()
+            outs, launches = {}, {}
             for name, v in (("auto", 0), ("fused", 1), ("warp", 2), ("lane", 3)):
                 _lib.check(L.txp_debug_set(0, v))
-                outs[name] = T.Format(fmt).compress(img, w, h, T.Params())
+                out = torch.zeros((w // 4) * (h // 4) * bs, dtype=torch.uint8, device="cuda")
+                n0 = T.kernel_launches()
+                _lib.check(L.txp_compress_device(fmt, ctypes.c_void_p(d.data_ptr()), w, h, ctypes.byref(cp), ctypes.c_void_p(out.data_ptr()), out.numel(), None))
+                torch.cuda.synchronize()
+                launches[name] = T.kernel_launches() - n0
+                outs[name] = out.cpu().numpy()
             _lib.check(L.txp_debug_set(0, 0))
             for name in ("fused", "warp", "lane"):
-                assert np.array_equal(outs["auto"], outs[name]), (kind, fmt, name)
+                assert np.array_equal(outs["auto"], outs[name]), (kind, fmt, alg, name)
+            assert launches["auto"] == launches["lane"], launches
+            assert launches["fused"] == 1 and launches["warp"] == 2, launches
 
 
+@pytest.mark.parametrize("alg", [1, 2])
 @pytest.mark.parametrize("fmt", [0, 2])
-def test_lane_mipchain(TL, fmt):
+def test_lane_mipchain(TL, fmt, alg):
     T = TL
     from texpresso_b200 import synth
     w, h = 200, 120
     img = synth.generate("smooth", w, h, seed=31)
-    tp = T.Params(T.Algorithm(1), tuple(O.PERCEPTUAL), False)
+    tp = T.Params(T.Algorithm(alg), tuple(O.PERCEPTUAL), False)
     got = T.compress_mipchain(fmt, img, w, h, tp)
-    op = O.make_params(1, O.PERCEPTUAL, False)
+    op = O.make_params(alg, O.PERCEPTUAL, False)
     want = np.concatenate([O.compress(fmt, lv, lv.shape[1], lv.shape[0], op) for lv in T.generate_mips(img, w, h)])
     assert np.array_equal(got, want)

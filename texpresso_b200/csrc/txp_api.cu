@@ -135,18 +135,17 @@ __global__ void __launch_bounds__(256) mip_downsample_kernel(const uint32_t* __r
 static thread_local std::string t_last_error;
 static std::atomic<uint64_t> g_launches{0};
 // ClusterFit kernel structure (tuning knob, txp_debug_set(0, v) or TXP_COLOUR_VARIANT=auto|fused|warp|lane):
-//  0 auto  : setup kernel + lane-per-block search (txp_cluster_lane.cuh) for ClusterFit launches of at least
-//            g_lane_min_blocks blocks, setup kernel + warp-per-block search otherwise (few blocks: the warp kernel has 32x
-//            the parallelism) and for IterativeClusterFit (per-block iteration counts differ)
+//  0 auto  : setup kernel + lane-per-block search (txp_cluster_lane.cuh) for launches of at least g_lane_min_blocks
+//            blocks, setup kernel + warp-per-block search otherwise (few blocks: the warp kernel has 32x the parallelism)
 //  1 fused : the original single warp-per-block kernel          2 warp : always setup + warp-per-block search
-//  3 lane  : setup + lane-per-block search for every non-iterative ClusterFit launch
+//  3 lane  : setup + lane-per-block search for every launch
 static std::atomic<int> g_colour_variant{[] {
     const char* v = getenv("TXP_COLOUR_VARIANT");
     const std::string s = v ? v : "";
     return s == "fused" ? 1 : s == "warp" ? 2 : s == "lane" ? 3 : 0;
 }()};
 static std::atomic<long long> g_lane_min_blocks{[] { const char* v = getenv("TXP_LANE_MIN_BLOCKS"); return v ? atoll(v) : 262144ll; }()};
-constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (284 B of scratch per block)
+constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (292 B of scratch per block)
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
 
@@ -366,30 +365,51 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
         const unsigned threads = COLOUR_WARPS * 32;
         const int variant = g_colour_variant.load(std::memory_order_relaxed);
-        const bool lane = e.algorithm == CLUSTER_FIT &&
-                          (variant == 3 || (variant == 0 && src.nblocks >= (uint64_t)g_lane_min_blocks.load(std::memory_order_relaxed)));
+        const bool lane = variant == 3 || (variant == 0 && src.nblocks >= (uint64_t)g_lane_min_blocks.load(std::memory_order_relaxed));
         if (lane) {
-            // K1 (thread per block, also emits the ordered weighted points) -> K2L (lane per block: search), in chunks
+            // K1 (thread per block; also emits the points of every colour set and a window-sorted permutation) ->
+            // K2L (lane per block: search), in chunks of LANE_CHUNK_BLOCKS blocks
             for (uint64_t first = 0; first < src.nblocks; first += LANE_CHUNK_BLOCKS) {
                 const uint32_t n = (uint32_t)std::min<uint64_t>(LANE_CHUNK_BLOCKS, src.nblocks - first);
                 const size_t n32 = ((size_t)n + 31) & ~size_t(31);
-                const size_t setup_bytes = n32 * sizeof(uint4), remap_bytes = n32 * sizeof(uint2), pw_bytes = n32 * 16 * sizeof(float4);
+                const size_t pt_bytes = n32 * 16 * sizeof(float4), setup_bytes = n32 * sizeof(uint4), remap_bytes = n32 * sizeof(uint2);
+                const size_t word_bytes = n32 * sizeof(uint32_t);
                 uint8_t* scratch = nullptr;
-                TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), setup_bytes + remap_bytes + pw_bytes + n32 * sizeof(uint32_t), ctx.pool, st));
-                float4* pw = reinterpret_cast<float4*>(scratch);
-                uint4* setup = reinterpret_cast<uint4*>(scratch + pw_bytes);
-                uint2* remap = reinterpret_cast<uint2*>(scratch + pw_bytes + setup_bytes);
-                uint32_t* perm = reinterpret_cast<uint32_t*>(scratch + pw_bytes + setup_bytes + remap_bytes);
+                TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), pt_bytes + setup_bytes + remap_bytes + 2 * word_bytes + 256, ctx.pool, st));
+                float4* pt = reinterpret_cast<float4*>(scratch);
+                uint4* setup = reinterpret_cast<uint4*>(scratch + pt_bytes);
+                uint2* remap = reinterpret_cast<uint2*>(scratch + pt_bytes + setup_bytes);
+                uint32_t* perm = reinterpret_cast<uint32_t*>(scratch + pt_bytes + setup_bytes + remap_bytes);
+                uint32_t* carry = perm + n32;
+                uint32_t* counters = carry + n32;
                 const unsigned g1 = (unsigned)((n + SETUP_WINDOW - 1) / SETUP_WINDOW), g2 = (unsigned)((n + LANE_THREADS - 1) / LANE_THREADS);
-                if (format == BC1) cluster_setup_sorted_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pw, perm, first, n);
-                else if (format == BC2) cluster_setup_sorted_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pw, perm, first, n);
-                else cluster_setup_sorted_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pw, perm, first, n);
-                if (format == BC1) cluster_lane_kernel<BC1><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pw, perm, d_out, first, n);
-                else if (format == BC2) cluster_lane_kernel<BC2><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pw, perm, d_out, first, n);
-                else cluster_lane_kernel<BC3><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pw, perm, d_out, first, n);
-                g_launches.fetch_add(2, std::memory_order_relaxed);
+                if (format == BC1) cluster_setup_sorted_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
+                else if (format == BC2) cluster_setup_sorted_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
+                else cluster_setup_sorted_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
+                cudaError_t aux_err = cudaSuccess;
+                if (e.algorithm == CLUSTER_FIT) {
+                    if (format == BC1) cluster_lane_kernel<BC1><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
+                    else if (format == BC2) cluster_lane_kernel<BC2><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
+                    else cluster_lane_kernel<BC3><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
+                    g_launches.fetch_add(2, std::memory_order_relaxed);
+                } else {
+                    // IterativeClusterFit: persistent warps draw blocks from a counter; BC1 = compress3 launch + compress4 launch
+                    aux_err = cudaMemsetAsync(counters, 0, 256, st);
+                    const unsigned cap = (unsigned)ctx.sm_count * TXP_LANE_ITER_MIN_CTAS, g3 = g2 < cap ? g2 : cap;
+                    if (format == BC1) {
+                        cluster_lane_iter_kernel<BC1, true><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+                        cluster_lane_iter_kernel<BC1, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters + 1, first, n);
+                        g_launches.fetch_add(1, std::memory_order_relaxed);
+                    } else if (format == BC2) {
+                        cluster_lane_iter_kernel<BC2, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+                    } else {
+                        cluster_lane_iter_kernel<BC3, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+                    }
+                    g_launches.fetch_add(2, std::memory_order_relaxed);
+                }
                 const cudaError_t launch_err = cudaGetLastError();
                 const cudaError_t free_err = cudaFreeAsync(scratch, st);    // stream-ordered: released after the search kernel
+                if (aux_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit memset: ") + cudaGetErrorString(aux_err));
                 if (launch_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit launch: ") + cudaGetErrorString(launch_err));
                 TXP_CUDA(free_err);
             }

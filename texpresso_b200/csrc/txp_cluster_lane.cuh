@@ -148,75 +148,260 @@ __device__ __forceinline__ float4 lane_range_sum(const float4* col, const int a,
     return acc;
 }
 
+// points_weights for the ordering `ow` (cluster.rs:123-133): colw[m] = (x, y, z, 1) * w of point ow[m]; zero guard at [count].
+// pt = the block's points in set order (global memory, written by the setup kernel).
+__device__ __forceinline__ void lane_build_pw(const float4* __restrict__ pt, const unsigned long long ow, const int count, float4* colw) {
+    for (int m = 0; m < count; ++m) {
+        const float4 q = __ldg(pt + ((ow >> (4 * m)) & 15ull));
+        colw[m * LANE_THREADS] = make_float4(mul(q.x, q.w), mul(q.y, q.w), mul(q.z, q.w), q.w);
+    }
+    colw[count * LANE_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+struct LaneWinner { bool three; int bi, bj, bk; };
+__device__ __forceinline__ LaneWinner lane_decode_key(const uint32_t key) {
+    LaneWinner w;
+    w.three = (key & 0x8000u) != 0;
+    w.bi = (int)((key >> (w.three ? 5 : 10)) & 31u);
+    w.bj = (int)((key >> (w.three ? 0 : 5)) & 31u);
+    w.bk = w.three ? w.bj : (int)(key & 31u);             // 3-colour: no third cluster (codes 0, 2, 1)
+    return w;
+}
+
+// the winning candidate once more, for its endpoints
+__device__ __forceinline__ void lane_winner_endpoints(const float4* col, const float4 xsum, const LaneWinner& w, const EncodeParams& prm, Solution& sol) {
+    const float4 p0 = lane_range_sum(col, 0, w.bi), p1 = lane_range_sum(col, w.bi, w.bj);
+    if (w.three) eval3_parts(p0, p1, xsum, prm.wx, prm.wy, prm.wz, &sol, true);
+    else eval4_parts(p0, p1, lane_range_sum(col, w.bj, w.bk), xsum, prm.wx, prm.wy, prm.wz, &sol, true);
+}
+
+// pack_565 of k*gridrcp is k itself (checked in tests/test_identities.py)
+__device__ __forceinline__ uint32_t lane_565(const float k[3]) { return ((uint32_t)k[0] << 11) | ((uint32_t)k[1] << 5) | (uint32_t)k[2]; }
+
+// remap + write3/write4 (cluster.rs:254-269 / :396-412, colourset.rs:130-141, colourblock.rs:55-94)
+__device__ __forceinline__ uint2 lane_finish_block(const unsigned long long ow, const int count, const LaneWinner& w, const uint32_t a565,
+                                                   const uint32_t b565, const uint2 rm, const uint32_t active16) {
+    // unordered[order[m]] = code(m), m ascending (later writes win)
+    uint32_t pc = 0;                                      // 2 bits per point
+    for (int m = 0; m < count; ++m) {
+        const uint32_t q = (uint32_t)(ow >> (4 * m)) & 15u;
+        const uint32_t cm = m < w.bi ? 0u : (m < w.bj ? 2u : (m < w.bk ? 3u : 1u));
+        pc = (pc & ~(3u << (2 * q))) | (cm << (2 * q));
+    }
+    uint32_t idx2 = 0;                                    // pixels without a point get index 3
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t p = ((i < 8 ? rm.x : rm.y) >> (4 * (i & 7))) & 15u;
+        const uint32_t c = ((active16 >> i) & 1u) ? ((pc >> (2 * p)) & 3u) : 3u;
+        idx2 |= c << (2 * i);
+    }
+    return w.three ? write3_packed(a565, b565, idx2) : write4_packed(a565, b565, idx2);
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_MIN_CTAS) cluster_lane_kernel(const EncodeParams prm,
                                                                                        const uint4* __restrict__ setup,
                                                                                        const uint2* __restrict__ remap,
-                                                                                       const float4* __restrict__ pwbuf,
+                                                                                       const float4* __restrict__ ptbuf,
                                                                                        const uint32_t* __restrict__ perm,
                                                                                        uint8_t* __restrict__ out,
                                                                                        const uint64_t first, const uint32_t n) {
     __shared__ float4 s_pw[17][LANE_THREADS];
     const int tid = threadIdx.x;
-    const float4* col = &s_pw[0][tid];
-    {
-        // perm is window-sorted by cluster_setup_sorted_kernel: 32 consecutive entries are blocks of (mostly) the same shape
-        const uint32_t slot = blockIdx.x * LANE_THREADS + tid;
-        if (slot >= n) return;
-        const uint32_t lb = __ldg(perm + slot);           // chunk-local block number
-        const uint4 su = __ldg(setup + lb);
-        if (!(su.z & SETUP_SEARCH)) return;               // finished by the setup kernel (0 or 1 points)
-        const int count = (int)(su.z & 31u);
-        for (int m = 0; m < count; ++m) s_pw[m][tid] = __ldg(pwbuf + pw_index(lb, m));
-        s_pw[count][tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 xsum = lane_range_sum(col, 0, count);                            // xsum_wsum (cluster.rs:125-133)
+    float4* col = &s_pw[0][tid];
+    // perm is window-sorted by cluster_setup_sorted_kernel: 32 consecutive entries are blocks of (mostly) the same shape
+    const uint32_t slot = blockIdx.x * LANE_THREADS + tid;
+    if (slot >= n) return;
+    const uint32_t lb = __ldg(perm + slot);               // chunk-local block number
+    const uint4 su = __ldg(setup + lb);
+    if (!(su.z & SETUP_SEARCH)) return;                   // finished by the setup kernel (0 or 1 points)
+    const int count = (int)(su.z & 31u);
+    const unsigned long long ow = (unsigned long long)su.x | ((unsigned long long)su.y << 32);
+    lane_build_pw(ptbuf + pt_index(lb, 0), ow, count, col);
+    const float4 xsum = lane_range_sum(col, 0, count);    // xsum_wsum (cluster.rs:125-133)
 
-        LaneBest best;
-        best.err = FLT_MAX;                                                           // cluster.rs:66
-        best.key = LANE_NONE;
-        if (FMT == BC1) {                                                             // colourfit.rs:48-59
-            lane_pass3(col, count, xsum, prm, best);
-            if (!(su.z & SETUP_TRANSPARENT)) lane_pass4(col, count, xsum, prm, best);
-        } else {
-            lane_pass4(col, count, xsum, prm, best);
-        }
+    LaneBest best;
+    best.err = FLT_MAX;                                   // cluster.rs:66
+    best.key = LANE_NONE;
+    if (FMT == BC1) {                                     // colourfit.rs:48-59
+        lane_pass3(col, count, xsum, prm, best);
+        if (!(su.z & SETUP_TRANSPARENT)) lane_pass4(col, count, xsum, prm, best);
+    } else {
+        lane_pass4(col, count, xsum, prm, best);
+    }
 
-        uint2 block = make_uint2(0u, 0u);                                             // best_compressed starts zeroed (cluster.rs:71)
-        if (best.key != LANE_NONE) {
-            const bool three = (best.key & 0x8000u) != 0;
-            const int bi = (int)((best.key >> (three ? 5 : 10)) & 31u), bj = (int)((best.key >> (three ? 0 : 5)) & 31u);
-            const int bk = three ? bj : (int)(best.key & 31u);     // 3-colour: no third cluster (codes 0, 2, 1)
-            // the winner once more, for its endpoints
-            Solution sol;
-            const float4 p0 = lane_range_sum(col, 0, bi), p1 = lane_range_sum(col, bi, bj);
-            if (three) eval3_parts(p0, p1, xsum, prm.wx, prm.wy, prm.wz, &sol, true);
-            else eval4_parts(p0, p1, lane_range_sum(col, bj, bk), xsum, prm.wx, prm.wy, prm.wz, &sol, true);
-            // unordered[order[m]] = code(m), m ascending (cluster.rs:254-262 / :396-405; later writes win)
-            const unsigned long long ow = (unsigned long long)su.x | ((unsigned long long)su.y << 32);
-            uint32_t pc = 0;                                                          // 2 bits per point
-            for (int m = 0; m < count; ++m) {
-                const uint32_t q = (uint32_t)(ow >> (4 * m)) & 15u;
-                const uint32_t cm = m < bi ? 0u : (m < bj ? 2u : (m < bk ? 3u : 1u));
-                pc = (pc & ~(3u << (2 * q))) | (cm << (2 * q));
-            }
-            // remap_indices (colourset.rs:130-141): pixels without a point get index 3
-            const uint2 rm = __ldg(remap + lb);
-            const uint32_t active16 = su.z >> 16;
-            uint32_t idx2 = 0;
+    uint2 block = make_uint2(0u, 0u);                     // best_compressed starts zeroed (cluster.rs:71)
+    if (best.key != LANE_NONE) {
+        const LaneWinner w = lane_decode_key(best.key);
+        Solution sol;
+        lane_winner_endpoints(col, xsum, w, prm, sol);
+        block = lane_finish_block(ow, count, w, lane_565(sol.ka), lane_565(sol.kb), __ldg(remap + lb), su.z >> 16);
+    }
+    uint2* out2 = reinterpret_cast<uint2*>(out);
+    const uint64_t b = first + lb;
+    if (FMT == BC1) out2[b] = block; else out2[2 * b + 1] = block;                    // lib.rs:213
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// IterativeClusterFit (cluster.rs:33, :59: up to 8 orderings per pass, each from the axis between the previous winner's
+// endpoints), one LANE per block.  Blocks need different numbers of orderings, so lanes do not own fixed blocks: every
+// warp draws 32-block chunks of the window-sorted permutation from a global counter and hands the next block to whichever
+// lane has finished its current one.  All lanes of a warp then run the same search (the loop nest of one pass) in lockstep.
+// The two passes of BC1 are two launches (THREE = compress3, then compress4 on the blocks without punch-through), with
+// best_error / best_compressed carried through `carry`, so that lanes in different passes never share a warp.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef TXP_LANE_ITER_MIN_CTAS
+#define TXP_LANE_ITER_MIN_CTAS 5
+#endif
+
+// construct_ordering (cluster.rs:78-105) for one thread: stable sort of (i, p_i . axis) for i < count, padding (0, f32::MAX)
+__device__ __forceinline__ unsigned long long lane_ordering(const float4* __restrict__ pt, const int count, const float ax, const float ay, const float az) {
+    int sk[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t p = ((i < 8 ? rm.x : rm.y) >> (4 * (i & 7))) & 15u;
-                const uint32_t c = ((active16 >> i) & 1u) ? ((pc >> (2 * p)) & 3u) : 3u;
-                idx2 |= c << (2 * i);
-            }
-            // pack_565 of k*gridrcp is k itself (checked in tests/test_identities.py)
-            const uint32_t a = ((uint32_t)sol.ka[0] << 11) | ((uint32_t)sol.ka[1] << 5) | (uint32_t)sol.ka[2];
-            const uint32_t b = ((uint32_t)sol.kb[0] << 11) | ((uint32_t)sol.kb[1] << 5) | (uint32_t)sol.kb[2];
-            block = three ? write3_packed(a, b, idx2) : write4_packed(a, b, idx2);
+    for (int e = 0; e < 16; ++e) {
+        int k = 0x7F7FFFFF;                               // f32::MAX, finite
+        if (e < count) {
+            const float4 q = __ldg(pt + e);
+            const uint32_t bits = __float_as_uint(add(add(mul(q.x, ax), mul(q.y, ay)), mul(q.z, az)));
+            // fcmp (cluster.rs:90-97): non-finite values compare Equal to each other and Greater than finite
+            if ((bits & 0x7F800000u) == 0x7F800000u) k = 0x7FFFFFFF;
+            else k = (bits & 0x80000000u) ? -(int)(bits & 0x7FFFFFFFu) : (int)bits;
         }
-        uint2* out2 = reinterpret_cast<uint2*>(out);
-        const uint64_t b = first + lb;
-        if (FMT == BC1) out2[b] = block; else out2[2 * b + 1] = block;                // lib.rs:213
+        sk[e] = k;
+    }
+    int rank[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) rank[e] = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+#pragma unroll
+        for (int f = e + 1; f < 16; ++f) {
+            const bool lt = sk[f] < sk[e];                // strict: on ties the earlier entry stays first
+            rank[e] += lt ? 1 : 0;
+            rank[f] += lt ? 0 : 1;
+        }
+    }
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        if (e < count) {                                  // padding entries carry index 0
+            if (rank[e] < 8) lo |= (uint32_t)e << (4 * rank[e]); else hi |= (uint32_t)e << (4 * (rank[e] - 8));
+        }
+    }
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+template <int FMT, bool THREE>
+__global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_ITER_MIN_CTAS) cluster_lane_iter_kernel(const EncodeParams prm,
+                                                                                                 const uint4* __restrict__ setup,
+                                                                                                 const uint2* __restrict__ remap,
+                                                                                                 const float4* __restrict__ ptbuf,
+                                                                                                 const uint32_t* __restrict__ perm,
+                                                                                                 uint32_t* __restrict__ carry,
+                                                                                                 uint8_t* __restrict__ out,
+                                                                                                 uint32_t* __restrict__ counter,
+                                                                                                 const uint64_t first, const uint32_t n) {
+    __shared__ float4 s_pw[17][LANE_THREADS];
+    __shared__ unsigned long long s_seen[8][LANE_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    float4* col = &s_pw[0][tid];
+    uint2* out2 = reinterpret_cast<uint2*>(out);
+
+    uint32_t pool = 0, pool_end = 0;                      // warp-uniform: the warp's current chunk of the permutation
+    bool exhausted = false;
+    // per-lane state of the block in progress
+    bool have = false;
+    uint32_t lb = 0, zflags = 0, best_key = LANE_NONE, a565 = 0, b565 = 0;
+    int count = 0, it = 0, best_it = 0;
+    float start_best = FLT_MAX, run_best = FLT_MAX;
+    float bsx = 0.f, bsy = 0.f, bsz = 0.f, bex = 0.f, bey = 0.f, bez = 0.f;
+    unsigned long long ow = 0, best_ow = 0;
+    float4 xsum = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (;;) {
+        // ---- give every idle lane its next block -------------------------------------------------------------------
+        for (;;) {
+            const uint32_t need = __ballot_sync(FULL, !have);
+            if (need == 0) break;
+            if (pool == pool_end) {
+                if (exhausted) break;
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(counter, 1u);
+                c = __shfl_sync(FULL, c, 0);
+                if ((uint64_t)c * 32 >= n) { exhausted = true; break; }
+                pool = c * 32;
+                pool_end = min(pool + 32u, n);
+            }
+            const uint32_t avail = pool_end - pool, idx = (uint32_t)__popc(need & ((1u << lane) - 1u));
+            if (!have && idx < avail) {
+                lb = __ldg(perm + pool + idx);
+                const uint4 su = __ldg(setup + lb);
+                bool ok = (su.z & SETUP_SEARCH) != 0;
+                if (FMT == BC1 && !THREE && (su.z & SETUP_TRANSPARENT)) ok = false;      // colourfit.rs:51
+                if (ok) {
+                    zflags = su.z;
+                    count = (int)(su.z & 31u);
+                    ow = (unsigned long long)su.x | ((unsigned long long)su.y << 32);  // iteration 0: the principal axis
+                    start_best = (FMT == BC1 && !THREE) ? __uint_as_float(__ldg(carry + lb)) : FLT_MAX;    // self.best_error
+                    run_best = start_best;
+                    it = 0; best_it = 0; best_key = LANE_NONE;
+                    bsx = bsy = bsz = bex = bey = bez = 0.f;                            // best_start = best_end = zero (:165-166 / :290-291)
+                    s_seen[0][tid] = ow;
+                    lane_build_pw(ptbuf + pt_index(lb, 0), ow, count, col);
+                    xsum = lane_range_sum(col, 0, count);
+                    have = true;
+                }
+            }
+            pool += min((uint32_t)__popc(need), avail);
+        }
+        if (!__any_sync(FULL, have)) break;
+
+        // ---- one search over the current ordering, all lanes in lockstep ---------------------------------------------
+        LaneBest best;
+        best.err = run_best;
+        best.key = LANE_NONE;
+        if (have) {
+            if (THREE) lane_pass3(col, count, xsum, prm, best);
+            else lane_pass4(col, count, xsum, prm, best);
+        }
+
+        // ---- bookkeeping of the reference's iteration loop (cluster.rs:171-249 / :298-389) ---------------------------
+        if (have) {
+            if (best.key != LANE_NONE) {                  // strictly better than everything before
+                run_best = best.err;
+                best_it = it; best_key = best.key; best_ow = ow;
+                Solution sol;
+                lane_winner_endpoints(col, xsum, lane_decode_key(best.key), prm, sol);
+                bsx = sol.ax; bsy = sol.ay; bsz = sol.az; bex = sol.bx; bey = sol.by; bez = sol.bz;
+                a565 = lane_565(sol.ka); b565 = lane_565(sol.kb);
+            }
+            bool finished = best_it != it;                // :243 / :383 (incl. quirk Q9: best_iteration starts at 0)
+            if (!finished) {
+                ++it;
+                if (it == 8) {
+                    finished = true;
+                } else {
+                    ow = lane_ordering(ptbuf + pt_index(lb, 0), count, sub(bex, bsx), sub(bey, bsy), sub(bez, bsz));    // :248 / :388
+                    for (int p = 0; p < it; ++p) finished |= (s_seen[p][tid] == ow);    // :108-120
+                    if (!finished) {
+                        s_seen[it][tid] = ow;
+                        lane_build_pw(ptbuf + pt_index(lb, 0), ow, count, col);
+                        xsum = lane_range_sum(col, 0, count);
+                    }
+                }
+            }
+            if (finished) {
+                const uint64_t b = first + lb;
+                uint2* dst = FMT == BC1 ? out2 + b : out2 + 2 * b + 1;                   // lib.rs:213
+                uint2 block = make_uint2(0u, 0u);          // best_compressed starts zeroed (cluster.rs:71)
+                const bool improved = run_best < start_best;                             // :252 / :392
+                if (improved)
+                    block = lane_finish_block(best_ow, count, lane_decode_key(best_key), a565, b565, __ldg(remap + lb), zflags >> 16);
+                if (improved || THREE || FMT != BC1) *dst = block;                       // compress4 of BC1 keeps compress3's block otherwise
+                if (FMT == BC1 && THREE) carry[lb] = __float_as_uint(run_best);
+                have = false;
+            }
+        }
     }
 }
 

@@ -8,9 +8,9 @@
 //   * Sym3x3::weighted_covariance + principle_component (math.rs:44-97)
 //   * construct_ordering for the principal axis (cluster.rs:78-105), which is iteration 0 of compress3 AND compress4
 // The warp-per-block search kernel (txp_colour.cuh) receives 16 bytes per block: the ordering word and flags.
-// With EMIT (lane-per-block search kernel, txp_cluster_lane.cuh) the thread also leaves the ordered weighted points
-// `points_weights` (cluster.rs:126-132) and the pixel -> point remap (colourset.rs:130-141), so that the search kernel
-// never touches the pixels.
+// With EMIT (lane-per-block search kernels, txp_cluster_lane.cuh) the thread also leaves the points of the set with
+// their weights (256 B) and the pixel -> point remap (colourset.rs:130-141), so that the search kernels never touch the
+// pixels.
 #pragma once
 #include "txp_range.cuh"
 
@@ -22,16 +22,16 @@ constexpr uint32_t SETUP_DEGENERATE = 0x200u;   // some projection is NaN/inf: o
 constexpr uint32_t SETUP_TRANSPARENT = 0x400u;  // BC1 punch-through pixels present: no 4-colour pass (colourfit.rs:51)
 // .z bits 0..4 = number of points, bits 16..31 = pixels that belong to a point (valid and not punched through)
 
-// ordered weighted points of chunk-local block lb, position m: 256 contiguous bytes per block (whole sectors per writer)
-__host__ __device__ __forceinline__ size_t pw_index(const uint32_t lb, const int m) { return (size_t)lb * 16 + m; }
+// point p of chunk-local block lb: 256 contiguous bytes per block (whole sectors per writer)
+__host__ __device__ __forceinline__ size_t pt_index(const uint32_t lb, const int p) { return (size_t)lb * 16 + p; }
 
 constexpr int SETUP_BINS = 35;                   // sort key: points (2..16) + 17 if punch-through; 34 = no search needed
 
 // One block, chunk-local number lb.  Returns the block's sort key.
 template <int FMT, bool EMIT>
 __device__ __forceinline__ int cluster_setup_block(const BlockSource& src, const EncodeParams& prm, uint8_t* __restrict__ out,
-                                                    uint4* __restrict__ setup, uint2* __restrict__ remap, float4* __restrict__ pwbuf,
-                                                    const float* lut, float4 (*uw)[128], const uint64_t first, const uint32_t lb) {
+                                                    uint4* __restrict__ setup, uint2* __restrict__ remap, float4* __restrict__ ptbuf,
+                                                    const float* lut, const uint64_t first, const uint32_t lb) {
     const uint64_t b = first + lb;
     uint32_t px[16];
     uint32_t mask;
@@ -113,18 +113,16 @@ __device__ __forceinline__ int cluster_setup_block(const BlockSource& src, const
             if (i < 8) rlo |= p << (4 * i); else rhi |= p << (4 * (i - 8));
         }
         remap[lb] = make_uint2(rlo, rhi);
-        // weighted points (cluster.rs:126-129: (x, y, z, 1) * w) in set order, then in the order of the principal axis
+        // the points of the set, in set order, with their weights (colourset.rs:65-67, :107-109); the search kernels form
+        // points_weights = (x, y, z, 1) * w in the order of the current axis themselves (cluster.rs:123-133)
         int p = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             if ((ts.new16 >> i) & 1u) {
-                const float x = lut[px[i] & 255u], y = lut[(px[i] >> 8) & 255u], z = lut[(px[i] >> 16) & 255u];
-                uw[p][threadIdx.x] = make_float4(mul(x, w[i]), mul(y, w[i]), mul(z, w[i]), w[i]);
+                ptbuf[pt_index(lb, p)] = make_float4(lut[px[i] & 255u], lut[(px[i] >> 8) & 255u], lut[(px[i] >> 16) & 255u], w[i]);
                 ++p;
             }
         }
-        const unsigned long long ow = (unsigned long long)lo | ((unsigned long long)hi << 32);
-        for (int m = 0; m < count; ++m) pwbuf[pw_index(lb, m)] = uw[(ow >> (4 * m)) & 15ull][threadIdx.x];
     }
     return count + (ts.transparent ? 17 : 0);
 }
@@ -139,7 +137,7 @@ __global__ void __launch_bounds__(128) cluster_setup_kernel(const BlockSource sr
     __syncthreads();
     const uint32_t lb = blockIdx.x * blockDim.x + threadIdx.x;
     if (lb >= n) return;
-    cluster_setup_block<FMT, false>(src, prm, out, setup, nullptr, nullptr, lut, nullptr, first, lb);
+    cluster_setup_block<FMT, false>(src, prm, out, setup, nullptr, nullptr, lut, first, lb);
 }
 
 // Setup for the lane-per-block search kernel.  One CTA owns a window of SETUP_WINDOW consecutive blocks (one block per
@@ -152,10 +150,9 @@ constexpr int SETUP_WINDOW = 128 * SETUP_WINDOW_ROUNDS;
 template <int FMT>
 __global__ void __launch_bounds__(128) cluster_setup_sorted_kernel(const BlockSource src, const EncodeParams prm,
                                                                    uint8_t* __restrict__ out, uint4* __restrict__ setup,
-                                                                   uint2* __restrict__ remap, float4* __restrict__ pwbuf,
+                                                                   uint2* __restrict__ remap, float4* __restrict__ ptbuf,
                                                                    uint32_t* __restrict__ perm, const uint64_t first, const uint32_t n) {
     __shared__ float lut[256];
-    __shared__ float4 uw[16][128];                        // weighted points in set order, one column per thread
     __shared__ int hist[SETUP_BINS];
     __shared__ uint16_t s_rank[SETUP_WINDOW];
     __shared__ uint8_t s_key[SETUP_WINDOW];
@@ -168,7 +165,7 @@ __global__ void __launch_bounds__(128) cluster_setup_sorted_kernel(const BlockSo
     for (int r = 0; r < SETUP_WINDOW_ROUNDS; ++r) {
         const uint32_t lb = win0 + r * 128 + tid;
         if (lb >= n) break;
-        const int key = cluster_setup_block<FMT, true>(src, prm, out, setup, remap, pwbuf, lut, uw, first, lb);
+        const int key = cluster_setup_block<FMT, true>(src, prm, out, setup, remap, ptbuf, lut, first, lb);
         s_key[r * 128 + tid] = (uint8_t)key;
         s_rank[r * 128 + tid] = (uint16_t)atomicAdd(&hist[key], 1);
     }
