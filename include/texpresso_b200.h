@@ -67,6 +67,19 @@ TXP_API size_t txp_compressed_size(int format, size_t width, size_t height);  /*
 TXP_API int txp_compress(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height,
                          const txp_params* params, uint8_t* output, size_t output_len);
 
+/* Extension: Format::compress on an image that is still in its decoded file layout.  The reference's
+ * CLI expands such images to RGBA8 on the host before compress (cli/src/image/png.rs:47-62, jpeg.rs:42-52):
+ * L8 -> (l, l, l, 255), LA8 -> (l, l, l, a), RGB8 -> (r, g, b, 255).  Here the 1-3 byte pixels are copied to the device
+ * as they are and expanded there (4x / 2x / 1.33x less host-to-device traffic: BC4 / BC5 are PCIe-bound through the host API).
+ * The result is byte-identical to expanding on the host and calling txp_compress.  Host pointers only. */
+#define TXP_PIXELS_L8 1
+#define TXP_PIXELS_LA8 2
+#define TXP_PIXELS_RGB8 3
+#define TXP_PIXELS_RGBA8 4
+#define TXP_PIXELS_RG8 5    /* no counterpart in the reference: (r, g) -> (r, g, 0, 255), two-channel normal maps for BC5 */
+TXP_API int txp_compress_pixels(int format, const uint8_t* pixels, size_t pixels_len, int layout, size_t width, size_t height,
+                                const txp_params* params, uint8_t* output, size_t output_len);
+
 /* Format::decompress, lib.rs:124-156.  data_len >= compressed_size, output_len >= 4*width*height. */
 TXP_API int txp_decompress(int format, const uint8_t* data, size_t data_len, size_t width, size_t height,
                            uint8_t* output, size_t output_len);

@@ -60,6 +60,15 @@ def test_cli_arguments_and_ingest(tmp_path):
     Image.fromarray(la, "LA").save(tmp_path / "la.png")
     rgba, _, _ = cli.read_image(tmp_path / "la.png")
     assert np.array_equal(rgba[..., 1], grey) and np.array_equal(rgba[..., 3], 255 - grey)
+    # read_pixels keeps the file layout (expanded on the device by compress_pixels); expand_pixels is its host statement
+    import texpresso_b200 as T
+    px, w, h = cli.read_pixels(tmp_path / "g.png")
+    assert px.shape == (3, 4, 1) and np.array_equal(T.expand_pixels(px, w, h), cli.read_image(tmp_path / "g.png")[0])
+    px, w, h = cli.read_pixels(tmp_path / "la.png")
+    assert px.shape == (3, 4, 2) and np.array_equal(T.expand_pixels(px, w, h), rgba)
+    Image.fromarray(np.dstack([grey, grey // 2, 255 - grey]), "RGB").save(tmp_path / "rgb.png")
+    px, w, h = cli.read_pixels(tmp_path / "rgb.png")
+    assert px.shape == (3, 4, 3) and np.array_equal(T.expand_pixels(px, w, h), cli.read_image(tmp_path / "rgb.png")[0])
 
 
 @pytest.mark.gpu

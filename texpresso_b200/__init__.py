@@ -147,6 +147,40 @@ def decompress_blocks(fmt, blocks):
     return out.reshape(n, 16, 4)
 
 
+PIXELS_L8, PIXELS_LA8, PIXELS_RGB8, PIXELS_RGBA8, PIXELS_RG8 = 1, 2, 3, 4, 5
+
+
+def compress_pixels(fmt, pixels, width, height, params=None, output=None, layout=None):
+    """Format.compress on an image in its decoded file layout: pixels is (h, w), (h, w, 1..4) or flat with 1-4 bytes per
+    pixel (L8, LA8, RGB8, RGBA8; layout=PIXELS_RG8 reads 2-byte pixels as (r, g, 0, 255) instead of gray + alpha).
+    Expansion to RGBA8 (cli/src/image/png.rs:47-62) happens on the device."""
+    pixels = _u8(pixels, "pixels")
+    npix = int(width) * int(height)
+    if npix == 0 or pixels.size % npix or not 1 <= pixels.size // npix <= 4:
+        raise ValueError("pixels must hold 1, 2, 3 or 4 bytes per pixel")
+    layout = pixels.size // npix if layout is None else int(layout)
+    params = params or Params()
+    if output is None:
+        output = np.empty(Format(fmt).compressed_size(width, height), dtype=np.uint8)
+    out = _u8(output, "output")
+    cp = params._c()
+    check(load().txp_compress_pixels(int(fmt), _ptr(pixels), pixels.size, layout, width, height, ctypes.byref(cp), _ptr(out), out.size))
+    return output
+
+
+def expand_pixels(pixels, width, height, layout=None):
+    """Host (numpy) statement of the expansion, for tests and tools (cli/src/image/png.rs:47-62)."""
+    pixels = np.asarray(pixels, dtype=np.uint8).reshape(height, width, -1)
+    c = pixels.shape[2]
+    out = np.empty((height, width, 4), np.uint8)
+    if c == 1: out[..., :3] = pixels; out[..., 3] = 255
+    elif c == 2 and layout == PIXELS_RG8: out[..., :2] = pixels; out[..., 2] = 0; out[..., 3] = 255
+    elif c == 2: out[..., :3] = pixels[..., :1]; out[..., 3] = pixels[..., 1]
+    elif c == 3: out[..., :3] = pixels; out[..., 3] = 255
+    else: out[...] = pixels
+    return out
+
+
 def shard_rows(height, rank, world):
     """Block-row range [begin, end) owned by `rank` of `world` (reference grain: one block row, lib.rs:300-305)."""
     a, b = ctypes.c_size_t(), ctypes.c_size_t()

@@ -9,7 +9,7 @@ SO_PATH = pathlib.Path(os.environ.get("TEXPRESSO_B200_LIB", HERE / "libtexpresso
 
 # every symbol include/texpresso_b200.h declares
 EXPORTS = [
-    "txp_num_blocks", "txp_block_size", "txp_compressed_size", "txp_compress", "txp_decompress",
+    "txp_num_blocks", "txp_block_size", "txp_compressed_size", "txp_compress", "txp_compress_pixels", "txp_decompress",
     "txp_compress_block_masked", "txp_decompress_block", "txp_compress_blocks", "txp_decompress_blocks",
     "txp_compress_device", "txp_decompress_device", "txp_shard_rows", "txp_compress_multi", "txp_compress_batch",
     "txp_mip_levels", "txp_mipchain_compressed_size", "txp_compress_mipchain", "txp_compress_batch_mips",
@@ -45,6 +45,7 @@ def load():
         "txp_block_size": (sz, [ci]),
         "txp_compressed_size": (sz, [ci, sz, sz]),
         "txp_compress": (ci, [ci, vp, sz, sz, sz, pp, vp, sz]),
+        "txp_compress_pixels": (ci, [ci, vp, sz, ci, sz, sz, pp, vp, sz]),
         "txp_decompress": (ci, [ci, vp, sz, sz, sz, vp, sz]),
         "txp_compress_block_masked": (ci, [ci, vp, u32, pp, vp, sz]),
         "txp_decompress_block": (ci, [ci, vp, sz, vp]),

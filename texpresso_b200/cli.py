@@ -10,7 +10,7 @@ mip chain to the DDS."""
 import argparse, pathlib, sys
 import numpy as np
 
-from . import Algorithm, Format, Params, COLOUR_WEIGHTS_PERCEPTUAL, compress_mipchain, mip_levels
+from . import Algorithm, Format, Params, COLOUR_WEIGHTS_PERCEPTUAL, compress_mipchain, compress_pixels, mip_levels
 from . import dds
 
 PROFILES = {"speed": Algorithm.RangeFit, "balanced": Algorithm.ClusterFit, "quality": Algorithm.IterativeClusterFit}   # main.rs:198-206
@@ -47,6 +47,22 @@ def read_image(path):
     return np.ascontiguousarray(rgba), im.width, im.height
 
 
+def read_pixels(path):
+    """-> (pixels uint8 (h, w, c), w, h) in the decoded file layout: c = 1 (gray), 2 (gray + alpha), 3 (RGB) or 4.  The
+    expansion to RGBA8 that cli/src/image/png.rs:47-62 does on the host is left to the device (compress_pixels)."""
+    from PIL import Image
+    ext = pathlib.Path(path).suffix.lower()
+    if ext not in (".png", ".jpg", ".jpeg"):
+        raise SystemExit("Unrecognized image format. Supported formats are PNG and JPEG")      # main.rs:136
+    im = Image.open(path)
+    if im.mode in ("I;16", "I;16B", "I"):
+        im = im.point(lambda v: v >> 8).convert("L")                                             # STRIP_16
+    if im.mode not in ("L", "LA", "RGB", "RGBA"):
+        im = im.convert("RGBA")                                                                  # EXPAND (palette, 1-bit, CMYK ...)
+    px = np.asarray(im, dtype=np.uint8).reshape(im.height, im.width, -1)
+    return np.ascontiguousarray(px), im.width, im.height
+
+
 def params_from_args(args):
     if not args.weights:
         w = COLOUR_WEIGHTS_PERCEPTUAL
@@ -62,13 +78,14 @@ def main(argv=None):
     if args.cmd == "compress":
         fmt = FORMATS[args.format]
         out = args.outfile or str(pathlib.Path(pathlib.Path(args.infile).name).with_suffix(".dds"))
-        rgba, w, h = read_image(args.infile)
         params = params_from_args(args)
         if args.mips:
+            rgba, w, h = read_image(args.infile)
             data = compress_mipchain(fmt, rgba, w, h, params)
             dds.write_dds(out, fmt, w, h, data, mip_levels=len(mip_levels(w, h)))
         else:
-            data = fmt.compress(rgba, w, h, params)
+            pixels, w, h = read_pixels(args.infile)          # 1-4 bytes per pixel; expanded to RGBA8 on the device
+            data = compress_pixels(fmt, pixels, w, h, params)
             dds.write_dds(out, fmt, w, h, data)
     else:
         from PIL import Image

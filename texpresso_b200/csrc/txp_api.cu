@@ -130,6 +130,27 @@ __global__ void __launch_bounds__(256) mip_downsample_kernel(const uint32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Channel expansion to RGBA8 on the device (the reference's CLI does this on the host before Format::compress,
+// cli/src/image/png.rs:47-62, jpeg.rs:42-52): L8 -> (l, l, l, 255), LA8 -> (l, l, l, a), RGB8 -> (r, g, b, 255).
+// One thread per pixel; a warp reads 32..96 contiguous bytes and writes 128.
+// ---------------------------------------------------------------------------------------------------
+// RG8 -> (r, g, 0, 255) has no counterpart in the reference (PNG has no two-channel colour type): it is the layout of
+// two-channel normal maps, what BC5 encodes (lib.rs:200-203 reads R and G only).
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) expand_pixels_kernel(const uint8_t* __restrict__ src, uint32_t* __restrict__ dst, const size_t npix) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    constexpr int BPP = LAYOUT == TXP_PIXELS_RG8 ? 2 : LAYOUT;
+    const uint8_t* p = src + i * BPP;
+    uint32_t v;
+    if (LAYOUT == TXP_PIXELS_L8) { const uint32_t l = __ldg(p); v = l * 0x00010101u | 0xFF000000u; }
+    else if (LAYOUT == TXP_PIXELS_LA8) { const uint32_t l = __ldg(p), a = __ldg(p + 1); v = l * 0x00010101u | (a << 24); }
+    else if (LAYOUT == TXP_PIXELS_RG8) { v = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | 0xFF000000u; }
+    else { v = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | 0xFF000000u; }
+    dst[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host runtime
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string t_last_error;
@@ -165,8 +186,8 @@ constexpr size_t MIN_CHUNK_BYTES = 2u << 20;    // smallest chunk worth a separa
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    uint8_t *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
-    size_t h_in_cap = 0, h_out_cap = 0, d_in_cap = 0, d_out_cap = 0;
+    uint8_t *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_raw = nullptr;
+    size_t h_in_cap = 0, h_out_cap = 0, d_in_cap = 0, d_out_cap = 0, d_raw_cap = 0;   // d_raw: 1-3 byte pixels before expansion
     // deferred copy of a staged result into a pageable caller buffer
     uint8_t* user_out = nullptr;
     size_t user_out_bytes = 0;
@@ -488,8 +509,11 @@ static int slot_wait(Slot& s) {
 
 // Encode block rows [row0,row1) (clipped to nblocks_total) of an image held in HOST memory on the
 // current device.  `out` points at the first byte of block row `row0`.
+// layout: TXP_PIXELS_RGBA8 = as the reference takes it; the other layouts are expanded on the device.
+static size_t layout_bpp(int layout) { return layout == TXP_PIXELS_RG8 ? 2 : (size_t)layout; }
 static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p,
-                              uint8_t* out, size_t row0, size_t row1, uint64_t blocks_in_range) {
+                              uint8_t* out, size_t row0, size_t row1, uint64_t blocks_in_range, const int layout = TXP_PIXELS_RGBA8) {
+    const size_t bpp = layout_bpp(layout);
     const size_t bs = (size_t)block_bytes(format), bw = (w + 3) / 4;
     const bool in_direct = dma_direct(rgba), out_direct = dma_direct(out);
     // at least ~6 chunks per call so that H2D, kernels and D2H of neighbouring chunks overlap (small shards at 8 ranks)
@@ -511,17 +535,29 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
         // pixel rows of this chunk that exist in the image (rows past h are fully masked)
         const size_t y0 = 4 * r, y1 = (4 * r_end < h) ? 4 * r_end : h;
         const size_t h_sub = y1 > y0 ? y1 - y0 : 0;
-        const size_t in_bytes = h_sub * w * 4, out_bytes = (size_t)nblk * bs;
-        if ((rc = grow_dev(&s.d_in, &s.d_in_cap, in_bytes ? in_bytes : 16)) != TXP_OK) break;
+        const size_t in_bytes = h_sub * w * bpp, out_bytes = (size_t)nblk * bs;
+        if ((rc = grow_dev(&s.d_in, &s.d_in_cap, h_sub * w * 4 ? h_sub * w * 4 : 16)) != TXP_OK) break;
         if ((rc = grow_dev(&s.d_out, &s.d_out_cap, out_bytes)) != TXP_OK) break;
+        if (bpp != 4 && (rc = grow_dev(&s.d_raw, &s.d_raw_cap, in_bytes ? in_bytes : 16)) != TXP_OK) break;
         if (in_bytes) {
-            const uint8_t* src_ptr = rgba + y0 * w * 4;
+            const uint8_t* src_ptr = rgba + y0 * w * bpp;
             if (!in_direct) {
                 if ((rc = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) break;
                 std::memcpy(s.h_in, src_ptr, in_bytes);
                 src_ptr = s.h_in;
             }
-            TXP_CUDA(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
+            TXP_CUDA(cudaMemcpyAsync(bpp == 4 ? s.d_in : s.d_raw, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
+            if (bpp != 4) {
+                const size_t npix = h_sub * w;
+                const unsigned g = (unsigned)((npix + 255) / 256);
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(s.d_in);
+                if (layout == TXP_PIXELS_L8) expand_pixels_kernel<TXP_PIXELS_L8><<<g, 256, 0, s.stream>>>(s.d_raw, d32, npix);
+                else if (layout == TXP_PIXELS_LA8) expand_pixels_kernel<TXP_PIXELS_LA8><<<g, 256, 0, s.stream>>>(s.d_raw, d32, npix);
+                else if (layout == TXP_PIXELS_RG8) expand_pixels_kernel<TXP_PIXELS_RG8><<<g, 256, 0, s.stream>>>(s.d_raw, d32, npix);
+                else expand_pixels_kernel<TXP_PIXELS_RGB8><<<g, 256, 0, s.stream>>>(s.d_raw, d32, npix);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                TXP_CUDA(cudaGetLastError());
+            }
         }
         const BlockSource bsrc = image_source(s.d_in, w, h_sub, nblk);
         if ((rc = launch_encode(c, format, bsrc, p, s.d_out, s.stream)) != TXP_OK) break;
@@ -686,6 +722,24 @@ int txp_decompress_device(int format, const void* d_data, size_t width, size_t h
     const uint64_t nblocks = (uint64_t)txp_num_blocks(width) * txp_num_blocks(height);
     return launch_decode(format, static_cast<const uint8_t*>(d_data), nblocks, (uint32_t)width, (uint32_t)height,
                          (uint32_t)txp_num_blocks(width), static_cast<uint8_t*>(d_output), static_cast<cudaStream_t>(cuda_stream));
+}
+
+int txp_compress_pixels(int format, const uint8_t* pixels, size_t pixels_len, int layout, size_t width, size_t height,
+                        const txp_params* params, uint8_t* output, size_t output_len) {
+    if (layout == TXP_PIXELS_RGBA8) return txp_compress(format, pixels, pixels_len, width, height, params, output, output_len);
+    if (layout < TXP_PIXELS_L8 || layout > TXP_PIXELS_RG8) return fail(TXP_ERR_ARGUMENT, "layout must be 1 (L8), 2 (LA8), 3 (RGB8), 4 (RGBA8) or 5 (RG8)");
+    int rc;
+    if (pixels_len < width * height * layout_bpp(layout)) return fail(TXP_ERR_BUFFER_TOO_SMALL, "pixels shorter than bytes_per_pixel*width*height");
+    // the remaining checks of Format::compress, on the expanded image
+    if ((rc = compress_checked(format, pixels, width * height * 4, width, height, params, output, output_len)) != TXP_OK) return rc;
+    if (is_device_ptr(pixels) || is_device_ptr(output)) return fail(TXP_ERR_ARGUMENT, "txp_compress_pixels takes host pointers");
+    DeviceCtx* c;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    const size_t bs = (size_t)block_bytes(format), bw = txp_num_blocks(width);
+    const uint64_t nblocks = output_len / bs;
+    const size_t rows = (size_t)((nblocks + bw - 1) / bw);
+    std::lock_guard<std::mutex> lk(c->mu);
+    return compress_host_rows(*c, format, pixels, width, height, params, output, 0, rows, nblocks, layout);
 }
 
 int txp_compress(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height, const txp_params* params,
