@@ -520,6 +520,12 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
     size_t chunk_bytes = (row1 - row0) * 16 * w / 6;
     if (chunk_bytes > CHUNK_BYTES) chunk_bytes = CHUNK_BYTES;
     if (chunk_bytes < MIN_CHUNK_BYTES) chunk_bytes = MIN_CHUNK_BYTES;
+    // ClusterFit searches are compute-bound (>= 1 ms per 16 MiB against 0.3 ms of H2D) and their lane-per-block kernels want
+    // launches of at least g_lane_min_blocks blocks: a shard that holds two or more such launches is not cut any finer
+    if (format <= BC3 && p->algorithm != RANGE_FIT) {
+        const size_t lane_bytes = (size_t)g_lane_min_blocks.load(std::memory_order_relaxed) * 64;
+        if (chunk_bytes < lane_bytes && lane_bytes <= CHUNK_BYTES && (row1 - row0) * 16 * w >= 2 * lane_bytes) chunk_bytes = lane_bytes;
+    }
     size_t rows_per_chunk = chunk_bytes / (16 * w);
     if (rows_per_chunk == 0) rows_per_chunk = 1;
     int rc = TXP_OK;
