@@ -1,2 +1,2 @@
-timeout 900 bash tools/gpu_sanitize.sh > gpurun_out/sanitizer_lane.txt 2>&1; cat gpurun_out/sanitizer_lane.txt
-python -m pytest tests/test_gpu_parity.py -x -q -k "multi_gpu or fullsize_8192 or thread_safe" 2>&1 | tail -2
+python -m pytest tests/test_gpu_cluster_lane.py -x -q 2>&1 | grep -v "^$" | cut -c1-1500 | tail -8
+python tools/size_sweep.py > gpurun_out/size_sweep2.jsonl 2>&1; tail -40 gpurun_out/size_sweep2.jsonl | cut -c1-170
