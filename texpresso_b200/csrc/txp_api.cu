@@ -179,7 +179,10 @@ static int fail(int code, const std::string& msg) { t_last_error = msg; return c
     } while (0)
 
 constexpr int MAX_DEVICES = 64;
-constexpr int NSLOTS = 3;
+#ifndef TXP_NSLOTS
+#define TXP_NSLOTS 6                // batches of 1024^2 textures: 3 -> 6 slots + lane kernels = +41 % textures/s (profiles/README.md)
+#endif
+constexpr int NSLOTS = TXP_NSLOTS;   // pipeline slots (stream + staging) per device
 constexpr size_t CHUNK_BYTES = 32u << 20;       // largest input chunk per pipeline stage
 constexpr size_t MIN_CHUNK_BYTES = 2u << 20;    // smallest chunk worth a separate launch + copy
 
@@ -331,7 +334,10 @@ static EncodeParams to_device_params(const txp_params* p) {
 }
 
 // ---- kernel launchers -------------------------------------------------------------------------------
-static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, const txp_params* p, uint8_t* d_out, cudaStream_t st) {
+// concurrent: the caller keeps several launches in flight on different streams (texture batches), so a launch does not
+// have to fill the GPU on its own for the lane-per-block kernels to pay off
+static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, const txp_params* p, uint8_t* d_out, cudaStream_t st,
+                         const bool concurrent = false) {
     if (src.nblocks == 0) return TXP_OK;
     if (src.nblocks > 0x3FFFFFFFull) return fail(TXP_ERR_DIMENSIONS, "more than 2^30-1 blocks in one launch");
     const EncodeParams e = to_device_params(p);
@@ -386,7 +392,8 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
         const unsigned threads = COLOUR_WARPS * 32;
         const int variant = g_colour_variant.load(std::memory_order_relaxed);
-        const bool lane = variant == 3 || (variant == 0 && src.nblocks >= (uint64_t)g_lane_min_blocks.load(std::memory_order_relaxed));
+        const uint64_t lane_min = (uint64_t)g_lane_min_blocks.load(std::memory_order_relaxed) / (concurrent ? 8 : 1);
+        const bool lane = variant == 3 || (variant == 0 && src.nblocks >= lane_min);
         if (lane) {
             // K1 (thread per block; also emits the points of every colour set and a window-sorted permutation) ->
             // K2L (lane per block: search), in chunks of LANE_CHUNK_BLOCKS blocks
@@ -617,7 +624,8 @@ static int mip_layout(int format, size_t w, size_t h, BlockSource* src, size_t* 
 }
 
 // enqueue H2D(level 0) -> mip kernels -> one encode launch -> D2H on slot s; the caller waits on the slot
-static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output) {
+static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
+                            const bool concurrent = false) {
     BlockSource src;
     size_t total_px = 0, total_out = 0;
     int n = mip_layout(format, w, h, &src, &total_px, &total_out);
@@ -642,7 +650,7 @@ static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* 
     TXP_CUDA(cudaGetLastError());
     src.rgba = s.d_in; src.masks = nullptr; src.w = (uint32_t)w; src.h = (uint32_t)h; src.bw = (uint32_t)txp_num_blocks(w);
     src.vec_ok = 1;                                       // cudaMalloc base; per-level width checked in locate_block
-    if ((rc = launch_encode(ctx, format, src, p, s.d_out, s.stream)) != TXP_OK) return rc;
+    if ((rc = launch_encode(ctx, format, src, p, s.d_out, s.stream, concurrent)) != TXP_OK) return rc;
     if (dma_direct(output)) {
         TXP_CUDA(cudaMemcpyAsync(output, s.d_out, total_out, cudaMemcpyDefault, s.stream));
     } else {
@@ -909,7 +917,7 @@ int txp_compress_batch_mips(int format, const uint8_t* const* rgba, const size_t
                 for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus, ++k) {   // copies overlap kernels
                     Slot& s = c->slots[k % NSLOTS];
                     if ((r = slot_wait(s)) != TXP_OK) break;
-                    r = mipchain_enqueue(*c, s, format, rgba[t], widths[t], heights[t], params, outputs[t]);
+                    r = mipchain_enqueue(*c, s, format, rgba[t], widths[t], heights[t], params, outputs[t], true);
                 }
                 for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
             }
