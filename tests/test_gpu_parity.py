@@ -265,6 +265,25 @@ def test_batch_with_mips_matches_single_calls(T):
         assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))
 
 
+@pytest.mark.parametrize("fmt,alg", [(0, 1), (2, 0), (3, 1), (1, 2)])
+def test_batch_matches_single_calls(T, fmt, alg):
+    """txp_compress_batch: textures pipelined through the slots (small ones) or the chunked path (> 32 MiB) give the bytes
+    of lone Format.compress calls, ragged sizes included."""
+    from texpresso_b200 import synth
+    tp, _ = _params(T, alg, O.PERCEPTUAL)
+    sizes = [(64, 32), (37, 23), (256, 256), (4, 4), (1, 7), (128, 20), (512, 64), (96, 96), (33, 3)]
+    if alg == 0:
+        sizes.append((4096, 2056))                           # > 32 MiB: chunked path in the middle of the batch
+        sizes.append((40, 40))
+    texs = [(synth.generate("smooth" if i % 2 else "noise_alpha", w, h, seed=300 + i), w, h) for i, (w, h) in enumerate(sizes)]
+    outs = T.compress_batch(fmt, texs, tp, n_gpus=1)
+    for (img, w, h), o in zip(texs, outs):
+        assert np.array_equal(o, T.Format(fmt).compress(img, w, h, tp)), (w, h)
+    if T.device_count() >= 2:
+        outs2 = T.compress_batch(fmt, texs, tp, n_gpus=2)
+        assert all(np.array_equal(a, b) for a, b in zip(outs, outs2))
+
+
 def test_concurrent_host_calls_are_thread_safe(T):
     """The C ABI is documented as thread-safe: several host threads encoding different images at once (ctypes drops the
     GIL) must each get the bytes a lone call produces."""

@@ -199,12 +199,13 @@ def compress_multi(fmt, rgba, width, height, params=None, n_gpus=1, output=None)
     return output
 
 
-def compress_batch(fmt, textures, params=None, n_gpus=1):
-    """textures: list of (rgba uint8 array, width, height); texture t is encoded on device t % n_gpus."""
+def compress_batch(fmt, textures, params=None, n_gpus=1, outputs=None):
+    """textures: list of (rgba uint8 array, width, height); texture t is encoded on device t % n_gpus.  Textures of up to
+    32 MiB are pipelined through the device's slots (copies and kernels of neighbouring textures overlap)."""
     params = params or Params()
     n = len(textures)
     arrs = [_u8(t[0], "rgba") for t in textures]
-    outs = [np.empty(Format(fmt).compressed_size(t[1], t[2]), dtype=np.uint8) for t in textures]
+    outs = outputs if outputs is not None else [np.empty(Format(fmt).compressed_size(t[1], t[2]), dtype=np.uint8) for t in textures]
     vp, sz = ctypes.c_void_p, ctypes.c_size_t
     ins = (vp * n)(*[a.ctypes.data for a in arrs])
     ous = (vp * n)(*[o.ctypes.data for o in outs])

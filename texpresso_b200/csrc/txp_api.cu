@@ -624,12 +624,19 @@ static int mip_layout(int format, size_t w, size_t h, BlockSource* src, size_t* 
 }
 
 // enqueue H2D(level 0) -> mip kernels -> one encode launch -> D2H on slot s; the caller waits on the slot
+// with_mips = false: level 0 only (a whole texture per slot: txp_compress_batch)
 static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
-                            const bool concurrent = false) {
+                            const bool concurrent = false, const bool with_mips = true) {
     BlockSource src;
     size_t total_px = 0, total_out = 0;
-    int n = mip_layout(format, w, h, &src, &total_px, &total_out);
-    if (n < 0) return n;
+    int n = 1;
+    if (with_mips) {
+        n = mip_layout(format, w, h, &src, &total_px, &total_out);
+        if (n < 0) return n;
+    } else {
+        total_px = w * h;
+        total_out = txp_compressed_size(format, w, h);
+    }
     int rc;
     if ((rc = grow_dev(&s.d_in, &s.d_in_cap, total_px * 4)) != TXP_OK) return rc;
     if ((rc = grow_dev(&s.d_out, &s.d_out_cap, total_out)) != TXP_OK) return rc;
@@ -648,8 +655,12 @@ static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* 
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     TXP_CUDA(cudaGetLastError());
-    src.rgba = s.d_in; src.masks = nullptr; src.w = (uint32_t)w; src.h = (uint32_t)h; src.bw = (uint32_t)txp_num_blocks(w);
-    src.vec_ok = 1;                                       // cudaMalloc base; per-level width checked in locate_block
+    if (with_mips) {
+        src.rgba = s.d_in; src.masks = nullptr; src.w = (uint32_t)w; src.h = (uint32_t)h; src.bw = (uint32_t)txp_num_blocks(w);
+        src.vec_ok = 1;                                   // cudaMalloc base; per-level width checked in locate_block
+    } else {
+        src = image_source(s.d_in, w, h, (uint64_t)txp_num_blocks(w) * txp_num_blocks(h));
+    }
     if ((rc = launch_encode(ctx, format, src, p, s.d_out, s.stream, concurrent)) != TXP_OK) return rc;
     if (dma_direct(output)) {
         TXP_CUDA(cudaMemcpyAsync(output, s.d_out, total_out, cudaMemcpyDefault, s.stream));
@@ -984,10 +995,30 @@ int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* wid
     for (int g = 0; g < n_gpus; ++g) {
         workers.emplace_back([&, g]() {
             int r = TXP_OK;
+            DeviceCtx* c = nullptr;
             if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
-            for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus) {
-                const size_t w = widths[t], h = heights[t];
-                r = txp_compress(format, rgba[t], w * h * 4, w, h, params, outputs[t], txp_compressed_size(format, w, h));
+            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            if (r == TXP_OK) {
+                std::lock_guard<std::mutex> lk(c->mu);
+                size_t k = 0;
+                for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus) {
+                    const size_t w = widths[t], h = heights[t];
+                    if ((r = check_dims(w, h)) != TXP_OK) break;
+                    if (!rgba[t] || !outputs[t]) { r = fail(TXP_ERR_ARGUMENT, "null texture pointer"); break; }
+                    if (h != 0 && w * h * 4 <= CHUNK_BYTES) {
+                        // a whole texture per pipeline slot: copies and kernels of neighbouring textures overlap
+                        Slot& s = c->slots[k++ % NSLOTS];
+                        if ((r = slot_wait(s)) != TXP_OK) break;
+                        r = mipchain_enqueue(*c, s, format, rgba[t], w, h, params, outputs[t], true, false);
+                    } else {
+                        // large texture: the chunked pipeline of txp_compress (it drains the slots itself at the end)
+                        for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
+                        if (r != TXP_OK) break;
+                        const size_t bw = txp_num_blocks(w), rows = txp_num_blocks(h);
+                        r = compress_host_rows(*c, format, rgba[t], w, h, params, outputs[t], 0, rows, (uint64_t)bw * rows);
+                    }
+                }
+                for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
             }
             rcs[(size_t)g] = r;
             if (r != TXP_OK) errs[(size_t)g] = t_last_error;

@@ -1,3 +1,13 @@
-for lib in texpresso_b200/libtexpresso_b200.so tools/micro/ab_lane/lib_s8.so; do echo "$lib (auto)"; for r in 1 2; do TEXPRESSO_B200_LIB=$lib python tools/bench_extra.py --mips 256 1 2>&1 | tail -1 | cut -c60-200; done; done
-python -m pytest tests/test_gpu_parity.py -x -q -k "mip or batch or image_encode or thread" 2>&1 | tail -2
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-120; python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e'])"
+python -m pytest tests/test_gpu_parity.py -x -q -k "batch or thread or multi" 2>&1 | tail -3
+python - <<'P'
+import time, numpy as np, torch, texpresso_b200 as T
+from texpresso_b200 import synth
+T.set_device(0)
+n = 256
+pinned = [torch.from_numpy(synth.generate("smooth", 1024, 1024, 6_000_000 + t).reshape(-1)).pin_memory() for t in range(n)]
+texs = [(p.numpy(), 1024, 1024) for p in pinned]
+for fmt, prm, name in ((T.Format.Bc3, T.Params(), "bc3_cluster"), (T.Format.Bc1, T.Params(T.Algorithm.RangeFit), "bc1_range"), (T.Format.Bc4, T.Params(), "bc4")):
+    T.compress_batch(fmt, texs, prm, n_gpus=1)
+    t0 = time.perf_counter(); T.compress_batch(fmt, texs, prm, n_gpus=1); dt = time.perf_counter() - t0
+    print(name, "batch 256 x 1024^2: %.1f ms, %.0f textures/s, %.0f Mpix/s" % (dt * 1e3, n / dt, n * 1.048576 / dt))
+P
