@@ -99,7 +99,7 @@ def test_lane_equals_warp_kernel_and_auto_threshold():
             _lib.check(L.txp_debug_set(0, 0))
             for name in ("fused", "warp", "lane"):
                 assert np.array_equal(outs["auto"], outs[name]), (kind, fmt, alg, name)
-            assert launches["auto"] == launches["lane"], launches
+            assert launches["auto"] == (launches["lane"] if alg == 1 else launches["warp"]), launches   # iterative: lane from 786432 blocks
             assert launches["fused"] == 1 and launches["warp"] == 2, launches
 
 
