@@ -71,6 +71,14 @@ public:
         compress(rgba.data(), rgba.size(), width, height, params, output.data(), output.size());
     }
 
+    /// Extension: compress() on an image in its decoded file layout (TXP_PIXELS_L8 / LA8 / RGB8 / RGBA8 / RG8); the expansion
+    /// the reference's CLI does on the host (cli/src/image/png.rs:47-62) runs on the device.
+    void compress_pixels(const uint8_t* pixels, std::size_t pixels_len, int layout, std::size_t width, std::size_t height,
+                         const Params& params, uint8_t* output, std::size_t output_len) const {
+        const txp_params p = params.c();
+        check(txp_compress_pixels(v_, pixels, pixels_len, layout, width, height, &p, output, output_len));
+    }
+
     /// lib.rs:124-156
     void decompress(const uint8_t* data, std::size_t data_len, std::size_t width, std::size_t height, uint8_t* output,
                     std::size_t output_len) const {

@@ -12,6 +12,8 @@ extern "C" {
     fn txp_compressed_size(format: c_int, width: usize, height: usize) -> usize;
     fn txp_compress(format: c_int, rgba: *const u8, rgba_len: usize, width: usize, height: usize,
                     params: *const TxpParams, output: *mut u8, output_len: usize) -> c_int;
+    fn txp_compress_pixels(format: c_int, pixels: *const u8, pixels_len: usize, layout: c_int, width: usize, height: usize,
+                           params: *const TxpParams, output: *mut u8, output_len: usize) -> c_int;
     fn txp_decompress(format: c_int, data: *const u8, data_len: usize, width: usize, height: usize,
                       output: *mut u8, output_len: usize) -> c_int;
     fn txp_compress_block_masked(format: c_int, rgba: *const u8, mask: u32, params: *const TxpParams,
@@ -22,6 +24,11 @@ extern "C" {
 
 #[derive(Clone, Copy, Debug, Eq, PartialEq)]
 pub enum Format { Bc1, Bc2, Bc3, Bc4, Bc5 }           // same order as texpresso::Format (lib.rs:40-46)
+
+/// Extension: the decoded file layouts the reference's CLI expands to RGBA8 on the host (cli/src/image/png.rs:47-62);
+/// `compress_pixels` expands them on the device instead.  `Rg8` = (r, g, 0, 255) has no counterpart in the reference.
+#[derive(Clone, Copy, Debug, Eq, PartialEq)]
+pub enum PixelLayout { L8 = 1, La8 = 2, Rgb8 = 3, Rgba8 = 4, Rg8 = 5 }
 
 fn c_params(p: Params) -> TxpParams {
     TxpParams {
@@ -47,6 +54,12 @@ impl Format {
     pub fn compress(self, rgba: &[u8], width: usize, height: usize, params: Params, output: &mut [u8]) {
         let p = c_params(params);
         check(unsafe { txp_compress(self.id(), rgba.as_ptr(), rgba.len(), width, height, &p, output.as_mut_ptr(), output.len()) });
+    }
+
+    /// `compress` on an image that is still in its decoded file layout (1-4 bytes per pixel).
+    pub fn compress_pixels(self, pixels: &[u8], layout: PixelLayout, width: usize, height: usize, params: Params, output: &mut [u8]) {
+        let p = c_params(params);
+        check(unsafe { txp_compress_pixels(self.id(), pixels.as_ptr(), pixels.len(), layout as c_int, width, height, &p, output.as_mut_ptr(), output.len()) });
     }
 
     pub fn decompress(self, data: &[u8], width: usize, height: usize, output: &mut [u8]) {
