@@ -179,6 +179,9 @@ static int fail(int code, const std::string& msg) { t_last_error = msg; return c
     } while (0)
 
 constexpr int MAX_DEVICES = 64;
+#ifndef TXP_HOST_CONCURRENT
+#define TXP_HOST_CONCURRENT 0      // 1: chunks of one image count as concurrent launches (lane kernels from 32768 blocks)
+#endif
 #ifndef TXP_NSLOTS
 #define TXP_NSLOTS 6                // batches of 1024^2 textures: 3 -> 6 slots + lane kernels = +41 % textures/s (profiles/README.md)
 #endif
@@ -576,7 +579,7 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
             }
         }
         const BlockSource bsrc = image_source(s.d_in, w, h_sub, nblk);
-        if ((rc = launch_encode(c, format, bsrc, p, s.d_out, s.stream)) != TXP_OK) break;
+        if ((rc = launch_encode(c, format, bsrc, p, s.d_out, s.stream, TXP_HOST_CONCURRENT != 0 && (row1 - row0) > 2 * rows_per_chunk)) != TXP_OK) break;
         uint8_t* dst = out + (r - row0) * bw * bs;
         if (out_direct) {
             TXP_CUDA(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
