@@ -115,3 +115,27 @@ def test_lane_mipchain(TL, fmt, alg):
     op = O.make_params(alg, O.PERCEPTUAL, False)
     want = np.concatenate([O.compress(fmt, lv, lv.shape[1], lv.shape[0], op) for lv in T.generate_mips(img, w, h)])
     assert np.array_equal(got, want)
+
+
+def test_lane_chunked_launch_equals_warp_kernel():
+    """More than 4 Mi blocks in one device-resident call: the lane path runs setup + search per chunk of 4 194 304 blocks
+    (scratch is 292 B per block); the second chunk starts at a non-zero block offset."""
+    import ctypes
+    import torch
+    import texpresso_b200 as T
+    from texpresso_b200 import synth, _lib
+    L = _lib.load()
+    w, h = 8192, 8200                                  # 2048 x 2050 = 4 198 400 blocks
+    d = torch.from_numpy(synth.generate("smooth", w, h, seed=41).reshape(-1)).cuda()
+    for fmt, alg in ((0, 1), (2, 2)):
+        bs = 8 if fmt == 0 else 16
+        cp = T.Params(T.Algorithm(alg))._c()
+        outs = {}
+        for name, v in (("warp", 2), ("auto", 0)):
+            _lib.check(L.txp_debug_set(0, v))
+            out = torch.zeros((w // 4) * (h // 4) * bs, dtype=torch.uint8, device="cuda")
+            _lib.check(L.txp_compress_device(fmt, ctypes.c_void_p(d.data_ptr()), w, h, ctypes.byref(cp), ctypes.c_void_p(out.data_ptr()), out.numel(), None))
+            torch.cuda.synchronize()
+            outs[name] = out
+        _lib.check(L.txp_debug_set(0, 0))
+        assert torch.equal(outs["warp"], outs["auto"]), (fmt, alg)
