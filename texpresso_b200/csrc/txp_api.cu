@@ -182,6 +182,9 @@ constexpr int MAX_DEVICES = 64;
 #ifndef TXP_HOST_CONCURRENT
 #define TXP_HOST_CONCURRENT 0      // 1: chunks of one image count as concurrent launches (lane kernels from 32768 blocks)
 #endif
+#ifndef TXP_SMALL_FIRST_CHUNK
+#define TXP_SMALL_FIRST_CHUNK 1
+#endif
 #ifndef TXP_NSLOTS
 #define TXP_NSLOTS 6                // batches of 1024^2 textures: 3 -> 6 slots + lane kernels = +41 % textures/s (profiles/README.md)
 #endif
@@ -544,8 +547,11 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
     int rc = TXP_OK;
     size_t chunk = 0;
     uint64_t blocks_left = blocks_in_range;
-    for (size_t r = row0; r < row1 && blocks_left > 0 && rc == TXP_OK; r += rows_per_chunk, ++chunk) {
-        const size_t r_end = (r + rows_per_chunk < row1) ? r + rows_per_chunk : row1;
+    // the first chunk's H2D copy is the one nothing overlaps: when there are several chunks, start with a quarter-sized one
+    const size_t first_rows = (TXP_SMALL_FIRST_CHUNK && (row1 - row0) >= 3 * rows_per_chunk && rows_per_chunk >= 4) ? rows_per_chunk / 4 : rows_per_chunk;
+    size_t step = first_rows;
+    for (size_t r = row0; r < row1 && blocks_left > 0 && rc == TXP_OK; r += step, step = rows_per_chunk, ++chunk) {
+        const size_t r_end = (r + step < row1) ? r + step : row1;
         uint64_t nblk = (uint64_t)(r_end - r) * bw;
         if (nblk > blocks_left) nblk = blocks_left;
         blocks_left -= nblk;
