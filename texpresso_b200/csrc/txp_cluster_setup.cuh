@@ -147,8 +147,11 @@ __global__ void __launch_bounds__(128) cluster_setup_kernel(const BlockSource sr
 constexpr int SETUP_WINDOW_ROUNDS = 8;
 constexpr int SETUP_WINDOW = 128 * SETUP_WINDOW_ROUNDS;
 
+#ifndef TXP_SETUP_MIN_CTAS
+#define TXP_SETUP_MIN_CTAS 4
+#endif
 template <int FMT>
-__global__ void __launch_bounds__(128) cluster_setup_sorted_kernel(const BlockSource src, const EncodeParams prm,
+__global__ void __launch_bounds__(128, TXP_SETUP_MIN_CTAS) cluster_setup_sorted_kernel(const BlockSource src, const EncodeParams prm,
                                                                    uint8_t* __restrict__ out, uint4* __restrict__ setup,
                                                                    uint2* __restrict__ remap, float4* __restrict__ ptbuf,
                                                                    uint32_t* __restrict__ perm, const uint64_t first, const uint32_t n) {
