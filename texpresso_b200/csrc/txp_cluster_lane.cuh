@@ -269,16 +269,15 @@ __device__ __forceinline__ unsigned long long lane_ordering(const float4* __rest
         }
         sk[e] = k;
     }
+    // rank[e] = e - (earlier entries that are larger) + (later entries that are smaller)
     int rank[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) rank[e] = 0;
+    for (int e = 0; e < 16; ++e) rank[e] = e;
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
 #pragma unroll
         for (int f = e + 1; f < 16; ++f) {
-            const bool lt = sk[f] < sk[e];                // strict: on ties the earlier entry stays first
-            rank[e] += lt ? 1 : 0;
-            rank[f] += lt ? 0 : 1;
+            if (sk[f] < sk[e]) { ++rank[e]; --rank[f]; }  // strict: on ties the earlier entry stays first
         }
     }
     uint32_t lo = 0, hi = 0;

@@ -78,16 +78,15 @@ __device__ __forceinline__ int cluster_setup_block(const BlockSource& src, const
         }
         sk[i] = k;
     }
+    // rank[e] = #{f < e: sk[f] <= sk[e]} + #{f > e: sk[f] < sk[e]} = e - (earlier entries that are larger) + (later entries that are smaller)
     int rank[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) rank[i] = 0;
+    for (int i = 0; i < 16; ++i) rank[i] = i;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
 #pragma unroll
         for (int j = i + 1; j < 16; ++j) {
-            const bool lt = sk[j] < sk[i];               // strict: on ties the earlier entry stays first
-            rank[i] += lt ? 1 : 0;
-            rank[j] += lt ? 0 : 1;
+            if (sk[j] < sk[i]) { ++rank[i]; --rank[j]; }   // strict: on ties the earlier entry stays first
         }
     }
     uint32_t lo = 0, hi = 0;
