@@ -118,6 +118,17 @@ TXP_API int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len,
 TXP_API int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* widths, const size_t* heights,
                                size_t n_textures, const txp_params* params, uint8_t* const* outputs, int n_gpus);
 
+/* Format::decompress (lib.rs:124-156) sharded like the reference's rayon loop over block rows (lib.rs:128-134): block rows
+ * are split with txp_shard_rows over devices 0..n_gpus-1, each device decodes its slice of `data` into its own pixel rows
+ * of `output`.  No collectives. */
+TXP_API int txp_decompress_multi(int format, const uint8_t* data, size_t data_len, size_t width, size_t height,
+                                 uint8_t* output, size_t output_len, int n_gpus);
+
+/* Batch of independent compressed textures, texture t -> device t % n_gpus; data[t] holds compressed_size(format, widths[t],
+ * heights[t]) bytes, outputs[t] receives 4*widths[t]*heights[t] bytes. */
+TXP_API int txp_decompress_batch(int format, const uint8_t* const* data, const size_t* widths, const size_t* heights,
+                                 size_t n_textures, uint8_t* const* outputs, int n_gpus);
+
 /* ---- mip chains (extension: the reference generates no mips, cli/src/main.rs:153) ------------------------------------ */
 /* Levels: (w,h), (max(1,w/2), max(1,h/2)), ... down to 1x1; each level is the 2x2 box filter (a+b+c+d+2)>>2 of the
  * previous one (edge-clamped), generated on the device.  Output: the levels' blocks concatenated, level 0 first. */
@@ -135,7 +146,12 @@ TXP_API int txp_set_device(int device);      /* cudaSetDevice for the calling th
 TXP_API const char* txp_last_error(void);    /* thread-local description of the last failure */
 TXP_API uint64_t txp_kernel_launches(void);  /* kernels launched by this library since load */
 TXP_API const char* txp_version(void);
-TXP_API int txp_debug_set(int key, int value);   /* tuning knobs for A/B measurements; key 0: ClusterFit kernel structure 0 auto, 1 fused, 2 warp per block, 3 lane per block; key 1: smallest launch (blocks) that takes the lane-per-block search in auto mode */
+TXP_API int txp_debug_get(int key, uint64_t* value);   /* key 0 / 1: the knobs above; 2 / 3 / 4: ClusterFit launches so far that took the lane-per-block search, the lane-per-block iterative search, the warp-per-block search (tests assert which structure an entry point reached) */
+/* Measurement helper for bench.py: rate of independent rounded fp32 products (FMUL, one lane-operation each) on the current
+ * device, in lane-operations per second -- the measured counterpart of SMs x 128 lanes x clock, the roof of the ClusterFit
+ * search under the reference's no-FMA-contraction contract. */
+TXP_API int txp_measure_fp32_issue(double* lane_ops_per_second);
+TXP_API int txp_debug_set(int key, int value);   /* tuning knobs for A/B measurements; key 0: ClusterFit kernel structure 0 auto, 1 fused, 2 warp per block, 3 lane per block; key 1: smallest launch (blocks) that takes the lane-per-block search in auto mode; key 0 value 4: full lane rounds + warp-per-block tail; key 2: tail threshold of that split in percent of a round (0 = off, default); key 3: host pipeline chunk size override in MiB (0 = automatic) */
 
 #ifdef __cplusplus
 }

@@ -88,7 +88,8 @@ def test_lane_equals_warp_kernel_and_auto_threshold():
             bs = 8 if fmt == 0 else 16
             cp = T.Params(T.Algorithm(alg))._c()
             outs, launches = {}, {}
-            for name, v in (("auto", 0), ("fused", 1), ("warp", 2), ("lane", 3)):
+            _lib.check(L.txp_debug_set(2, 100))               # hybrid: every partly filled last round goes to the warp kernel
+            for name, v in (("auto", 0), ("fused", 1), ("warp", 2), ("lane", 3), ("hybrid", 4)):
                 _lib.check(L.txp_debug_set(0, v))
                 out = torch.zeros((w // 4) * (h // 4) * bs, dtype=torch.uint8, device="cuda")
                 n0 = T.kernel_launches()
@@ -97,7 +98,8 @@ def test_lane_equals_warp_kernel_and_auto_threshold():
                 launches[name] = T.kernel_launches() - n0
                 outs[name] = out.cpu().numpy()
             _lib.check(L.txp_debug_set(0, 0))
-            for name in ("fused", "warp", "lane"):
+            _lib.check(L.txp_debug_set(2, 0))
+            for name in ("fused", "warp", "lane", "hybrid"):
                 assert np.array_equal(outs["auto"], outs[name]), (kind, fmt, alg, name)
             assert launches["auto"] == (launches["lane"] if alg == 1 else launches["warp"]), launches   # iterative: lane from 786432 blocks
             assert launches["fused"] == 1 and launches["warp"] == 2, launches

@@ -73,20 +73,11 @@ def test_rangefit_blocks_bit_exact(T, fmt, wname, awa):
 @pytest.mark.parametrize("alg", [1, 2])
 @pytest.mark.parametrize("fmt", [0, 1, 2])
 def test_clusterfit_blocks(T, fmt, alg, wname, awa):
+    """Default (warp-per-block) ClusterFit / IterativeClusterFit path on the stratified corpus: bit-exact, as DESIGN.md and
+    INTEGRATION.md claim (the north star's >= 99.9 % tolerance is not used: there are no known divergent blocks)."""
     blocks, masks, tags = blockgen.colour_cases()
     got, want, diff, op = _compare_blocks(T, fmt, blocks, masks, tags, alg, wname, awa)
-    frac = 1.0 - diff.size / len(blocks)
-    off = 0 if fmt == 0 else 8
-    worse = []
-    for i in diff:
-        # alpha halves must still be bit exact
-        assert bytes(got[i][:off]) == bytes(want[i][:off]), (tags[i], "alpha half differs")
-        eg = O.colour_block_error(fmt, blocks[i], int(masks[i]), op, got[i][off:off + 8])
-        ew = O.colour_block_error(fmt, blocks[i], int(masks[i]), op, want[i][off:off + 8])
-        if eg > ew * (1 + 1e-6) + 1e-12:
-            worse.append((int(i), tags[i], eg, ew, bytes(got[i]).hex(), bytes(want[i]).hex()))
-    assert not worse, worse[:5]
-    assert frac >= 0.999, (frac, [(int(i), tags[i], bytes(got[i]).hex(), bytes(want[i]).hex()) for i in diff[:8]])
+    assert diff.size == 0, [(int(i), tags[i], bytes(got[i]).hex(), bytes(want[i]).hex()) for i in diff[:8]]
 
 
 @pytest.mark.parametrize("fmt", [2, 3, 4])
@@ -307,3 +298,95 @@ def test_concurrent_host_calls_are_thread_safe(T):
     [t.start() for t in ts]; [t.join() for t in ts]
     assert not errs, errs
     assert all(np.array_equal(g, e) for g, e in zip(got, expect))
+
+
+# ---- round 2: host-API kernel selection, decode sharding / batching ------------------------------------------------
+def _debug_get(key):
+    import ctypes
+    from texpresso_b200 import _lib
+    v = ctypes.c_uint64(0)
+    _lib.check(_lib.load().txp_debug_get(key, ctypes.byref(v)))
+    return v.value
+
+
+def test_fullsize_8192_bc1_iterative_auto_path_vs_oracle(T):
+    """BASELINE config 3 through the public host API: the pipeline chunks must be large enough for the lane-per-block
+    iterative kernels (>= 786 432 blocks per launch), and the bytes must equal the oracle's on slices of the full-size output --
+    including blocks in the quarter-sized first chunk (warp-per-block kernel) and in later chunks (lane kernels, BC1 carry path)."""
+    from texpresso_b200 import synth
+    w = h = 8192
+    img = synth.generate("noise_opaque", w, h, seed=3)
+    tp, op = _params(T, 2, O.PERCEPTUAL)
+    lane0, warp0 = _debug_get(3), _debug_get(4)
+    a = T.Format.Bc1.compress(img, w, h, tp)
+    lane, warp = _debug_get(3) - lane0, _debug_get(4) - warp0
+    assert lane >= 4 and warp <= 1, (lane, warp)             # 5-6 chunks of 384 block rows, the first one quarter-sized
+    rowbytes = (w // 4) * 8
+    for y0 in (0, 1024, 4096 + 512, h - 32):                  # first chunk, chunk interiors, last rows
+        want = O.compress(0, img[y0:y0 + 32, :2048], 2048, 32, op, threads=8).reshape(8, -1)
+        got = a[(y0 // 4) * rowbytes:(y0 // 4 + 8) * rowbytes].reshape(8, rowbytes)[:, :512 * 8]
+        nd = int((got.reshape(-1, 8) != want.reshape(-1, 8)).any(axis=1).sum())
+        assert nd == 0, (y0, nd)
+    # the device-pointer entry point (one launch over 4 Mi blocks) produces the same bytes
+    import torch, ctypes
+    from texpresso_b200 import _lib
+    d_in = torch.from_numpy(img.reshape(-1)).cuda()
+    d_out = torch.empty(a.size, dtype=torch.uint8, device="cuda")
+    cp = tp._c()
+    _lib.check(_lib.load().txp_compress_device(0, ctypes.c_void_p(d_in.data_ptr()), w, h, ctypes.byref(cp), ctypes.c_void_p(d_out.data_ptr()),
+                                               d_out.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), a)
+
+
+def test_lane_chunk_rows_round_up(T):
+    """Widths for which 16 MiB is not a whole number of block rows still reach the lane-per-block kernels (chunk rows are rounded up)."""
+    from texpresso_b200 import synth
+    w, h = 6000, 1600                                         # 1500 blocks per row: 174 rows would be 261 000 < 262 144
+    img = synth.generate("noise_opaque", w, h, seed=12)
+    tp, op = _params(T, 1, O.PERCEPTUAL)
+    lane0 = _debug_get(2)
+    a = T.Format.Bc1.compress(img, w, h, tp)
+    assert _debug_get(2) - lane0 >= 2
+    want = O.compress(0, img[800:832], w, 32, op, threads=8)
+    assert np.array_equal(a[200 * 1500 * 8:208 * 1500 * 8], want)
+
+
+@pytest.mark.parametrize("fmt", range(5))
+def test_decompress_multi_and_batch(T, fmt):
+    from texpresso_b200 import synth
+    tp, _ = _params(T, 0, O.PERCEPTUAL)
+    sizes = [(1024, 1000), (37, 23), (256, 64), (4, 4), (1, 7), (2048, 1030)]
+    texs = [(synth.generate("smooth" if i % 2 else "noise_alpha", w, h, seed=500 + i), w, h) for i, (w, h) in enumerate(sizes)]
+    enc = [T.Format(fmt).compress(img, w, h, tp) for img, w, h in texs]
+    want = [O.decompress(fmt, e, w, h) for e, (_, w, h) in zip(enc, texs)]
+    for n in sorted({1, min(2, T.device_count()), T.device_count()}):
+        for e, (_, w, h), wnt in zip(enc, texs, want):
+            assert np.array_equal(T.decompress_multi(fmt, e, w, h, n_gpus=n), wnt), (w, h, n)
+        got = T.decompress_batch(fmt, [(e, w, h) for e, (_, w, h) in zip(enc, texs)], n_gpus=n)
+        assert all(np.array_equal(g, wnt) for g, wnt in zip(got, want)), n
+
+
+def test_decompress_large_pipelined(T):
+    """Format.decompress on an image of several pipeline chunks (ragged height) equals the oracle."""
+    from texpresso_b200 import synth
+    w, h = 4096, 4090
+    img = synth.generate("noise_alpha", w, h, seed=21)
+    enc = T.Format.Bc3.compress(img, w, h, T.Params(T.Algorithm.RangeFit))
+    assert np.array_equal(T.Format.Bc3.decompress(enc, w, h), O.decompress(2, enc, w, h))
+
+
+def test_multi_gpu_all_entry_points(T):
+    """txp_compress_multi / txp_compress_batch{,_mips} / txp_decompress_{multi,batch} with n_gpus >= 2 (skipped on a 1-GPU box;
+    bench.py runs the same comparison under torchrun: `multi_matches_single`)."""
+    if T.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from texpresso_b200 import synth
+    n = T.device_count()
+    w, h = 4096, 4090
+    img = synth.generate("noise_alpha", w, h, seed=31)
+    for fmt, alg in ((0, 1), (2, 2), (4, 1)):
+        tp, _ = _params(T, alg, O.PERCEPTUAL)
+        one = T.Format(fmt).compress(img, w, h, tp)
+        assert np.array_equal(T.compress_multi(fmt, img, w, h, tp, n_gpus=n), one)
+        assert np.array_equal(T.decompress_multi(fmt, one, w, h, n_gpus=n), T.Format(fmt).decompress(one, w, h))

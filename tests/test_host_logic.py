@@ -95,3 +95,38 @@ def test_generate_mips_box_filter():
     assert np.array_equal(lv[1][0, 0], (a[0, 0] + a[0, 1] + a[1, 0] + a[1, 1] + 2) >> 2)
     b = lv[1].astype(np.int32)                       # 3 wide -> 1 wide: columns 0,1 (clamped sampling never reaches col 2)
     assert np.array_equal(lv[2][0, 0], (b[0, 0] + b[0, 1] + b[1, 0] + b[1, 1] + 2) >> 2)
+
+
+def test_batch_wrappers_validate_sizes_before_calling_c():
+    """the batch entry points take no buffer lengths, so the Python mirror must reject short / strided buffers itself.
+    These raise before any C call, i.e. they run without a GPU."""
+    import numpy as np
+    import pytest
+    import texpresso_b200 as T
+    good = np.zeros(16 * 16 * 4, np.uint8)
+    with pytest.raises(ValueError):
+        T.compress_batch(0, [(good[:100], 16, 16)])
+    with pytest.raises(ValueError):
+        T.compress_batch(0, [(good, 16, 16)], outputs=[np.zeros(8, np.uint8)])
+    with pytest.raises(ValueError):
+        T.compress_batch(0, [(good, 16, 16)], outputs=[np.zeros(256, np.uint8)[::2]])
+    with pytest.raises(ValueError):
+        T.compress_batch_mips(2, [(good[:100], 16, 16)])
+    with pytest.raises(ValueError):
+        T.compress_batch_mips(2, [(good, 16, 16)], outputs=[np.zeros(16, np.uint8)])
+    with pytest.raises(ValueError):
+        T.decompress_batch(0, [(np.zeros(8, np.uint8), 16, 16)])
+    with pytest.raises(ValueError):
+        T.compress_batch(0, [(good, 16, 16), (good, 16, 16)], outputs=[np.zeros(128, np.uint8)])
+    for fn in (lambda o: T.compress_pixels(0, good, 16, 16, output=o), lambda o: T.compress_multi(0, good, 16, 16, output=o),
+               lambda o: T.Format.Bc1.compress_block_masked(good[:64], 0xFFFF, output=o), lambda o: T.decompress_multi(0, np.zeros(128, np.uint8), 16, 16, output=o)):
+        with pytest.raises(ValueError):
+            fn(np.zeros(4096, np.uint8)[::2])               # non-contiguous output: would be written through a temporary copy
+
+
+def test_debug_knobs_reject_bad_values():
+    from texpresso_b200 import _lib
+    L = _lib.load()
+    assert L.txp_debug_set(1, -5) != 0
+    assert L.txp_debug_set(1, 0) != 0
+    assert L.txp_debug_set(0, 7) != 0

@@ -20,7 +20,7 @@ import numpy as np
 from ._lib import CParams, TexpressoError, check, load
 
 __all__ = ["Format", "Algorithm", "Params", "ColourWeights", "COLOUR_WEIGHTS_UNIFORM", "COLOUR_WEIGHTS_PERCEPTUAL",
-           "num_blocks", "TexpressoError", "shard_rows", "compress_multi", "compress_batch", "compress_blocks",
+           "num_blocks", "TexpressoError", "shard_rows", "compress_multi", "compress_batch", "decompress_multi", "decompress_batch", "compress_blocks",
            "decompress_blocks", "mip_levels", "generate_mips", "compress_mipchain", "compress_batch_mips", "device_count", "set_device", "kernel_launches", "version"]
 
 ColourWeights = tuple
@@ -64,6 +64,14 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def _out(output, name="output"):
+    """A caller-supplied output must be written in place: contiguous uint8, no temporary copy."""
+    out = _u8(output, name)
+    if not np.shares_memory(out, output):
+        raise ValueError(f"{name} must be a contiguous uint8 array")
+    return out
+
+
 class Format(enum.IntEnum):                              # lib.rs:39-46
     Bc1 = 0
     Bc2 = 1
@@ -84,9 +92,7 @@ class Format(enum.IntEnum):                              # lib.rs:39-46
         params = params or Params()
         if output is None:
             output = np.empty(self.compressed_size(width, height), dtype=np.uint8)
-        out = _u8(output, "output")
-        if not np.shares_memory(out, output):
-            raise ValueError("output must be a contiguous uint8 array")
+        out = _out(output)
         cp = params._c()
         check(load().txp_compress(int(self), _ptr(rgba), rgba.size, width, height, ctypes.byref(cp), _ptr(out), out.size))
         return output
@@ -96,9 +102,7 @@ class Format(enum.IntEnum):                              # lib.rs:39-46
         data = _u8(data, "data")
         if output is None:
             output = np.empty(width * height * 4, dtype=np.uint8)
-        out = _u8(output, "output")
-        if not np.shares_memory(out, output):
-            raise ValueError("output must be a contiguous uint8 array")
+        out = _out(output)
         check(load().txp_decompress(int(self), _ptr(data), data.size, width, height, _ptr(out), out.size))
         return output
 
@@ -110,7 +114,7 @@ class Format(enum.IntEnum):                              # lib.rs:39-46
         params = params or Params()
         if output is None:
             output = np.empty(self.block_size(), dtype=np.uint8)
-        out = _u8(output, "output")
+        out = _out(output)
         cp = params._c()
         check(load().txp_compress_block_masked(int(self), _ptr(rgba), int(mask) & 0xFFFFFFFF, ctypes.byref(cp), _ptr(out), out.size))
         return output
@@ -162,7 +166,7 @@ def compress_pixels(fmt, pixels, width, height, params=None, output=None, layout
     params = params or Params()
     if output is None:
         output = np.empty(Format(fmt).compressed_size(width, height), dtype=np.uint8)
-    out = _u8(output, "output")
+    out = _out(output)
     cp = params._c()
     check(load().txp_compress_pixels(int(fmt), _ptr(pixels), pixels.size, layout, width, height, ctypes.byref(cp), _ptr(out), out.size))
     return output
@@ -193,27 +197,68 @@ def compress_multi(fmt, rgba, width, height, params=None, n_gpus=1, output=None)
     params = params or Params()
     if output is None:
         output = np.empty(Format(fmt).compressed_size(width, height), dtype=np.uint8)
-    out = _u8(output, "output")
+    out = _out(output)
     cp = params._c()
     check(load().txp_compress_multi(int(fmt), _ptr(rgba), rgba.size, width, height, ctypes.byref(cp), _ptr(out), out.size, n_gpus))
     return output
+
+
+def decompress_multi(fmt, data, width, height, n_gpus=1, output=None):
+    """Format.decompress with the block rows sharded over n_gpus devices (reference grain: lib.rs:128-134)."""
+    data = _u8(data, "data")
+    if output is None:
+        output = np.empty(int(width) * int(height) * 4, dtype=np.uint8)
+    out = _out(output)
+    check(load().txp_decompress_multi(int(fmt), _ptr(data), data.size, width, height, _ptr(out), out.size, n_gpus))
+    return output
+
+
+def _batch_args(textures, need_in, need_out, outputs):
+    """Checks every (array, width, height) of a batch against the sizes the C ABI will read / write (it takes no lengths)."""
+    n = len(textures)
+    arrs = []
+    for t, (a, w, h) in enumerate(textures):
+        a = _u8(a, f"textures[{t}]")
+        if int(w) <= 0 or int(h) < 0:
+            raise ValueError(f"textures[{t}]: bad dimensions {w}x{h}")
+        if a.size < need_in(int(w), int(h)):
+            raise ValueError(f"textures[{t}]: {a.size} bytes, {need_in(int(w), int(h))} needed for {w}x{h}")
+        arrs.append(a)
+    if outputs is None:
+        outputs = [np.empty(need_out(int(t[1]), int(t[2])), dtype=np.uint8) for t in textures]
+    if len(outputs) != n:
+        raise ValueError("outputs must hold one array per texture")
+    outs = []
+    for t, o in enumerate(outputs):
+        oo = _out(o, f"outputs[{t}]")
+        if oo.size < need_out(int(textures[t][1]), int(textures[t][2])):
+            raise ValueError(f"outputs[{t}]: {oo.size} bytes, {need_out(int(textures[t][1]), int(textures[t][2]))} needed")
+        outs.append(oo)
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    ins = (vp * n)(*[a.ctypes.data for a in arrs])
+    ous = (vp * n)(*[o.ctypes.data for o in outs])
+    ws = (sz * n)(*[int(t[1]) for t in textures])
+    hs = (sz * n)(*[int(t[2]) for t in textures])
+    return n, arrs, outputs, ins, ous, ws, hs
+
+
+def decompress_batch(fmt, textures, n_gpus=1, outputs=None):
+    """textures: list of (compressed uint8 array, width, height); texture t is decoded on device t % n_gpus."""
+    f = Format(fmt)
+    n, _keep, outputs, ins, ous, ws, hs = _batch_args(textures, lambda w, h: f.compressed_size(w, h), lambda w, h: 4 * w * h, outputs)
+    check(load().txp_decompress_batch(int(fmt), ins, ws, hs, n, ous, n_gpus))
+    return outputs
 
 
 def compress_batch(fmt, textures, params=None, n_gpus=1, outputs=None):
     """textures: list of (rgba uint8 array, width, height); texture t is encoded on device t % n_gpus.  Textures of up to
     32 MiB are pipelined through the device's slots (copies and kernels of neighbouring textures overlap)."""
     params = params or Params()
-    n = len(textures)
-    arrs = [_u8(t[0], "rgba") for t in textures]
-    outs = outputs if outputs is not None else [np.empty(Format(fmt).compressed_size(t[1], t[2]), dtype=np.uint8) for t in textures]
-    vp, sz = ctypes.c_void_p, ctypes.c_size_t
-    ins = (vp * n)(*[a.ctypes.data for a in arrs])
-    ous = (vp * n)(*[o.ctypes.data for o in outs])
-    ws = (sz * n)(*[t[1] for t in textures])
-    hs = (sz * n)(*[t[2] for t in textures])
+    f = Format(fmt)
+    n, _keep, outputs, ins, ous, ws, hs = _batch_args(textures, lambda w, h: 4 * w * h, lambda w, h: f.compressed_size(w, h), outputs)
     cp = params._c()
     check(load().txp_compress_batch(int(fmt), ins, ws, hs, n, ctypes.byref(cp), ous, n_gpus))
-    return outs
+    return outputs
 
 
 def mip_levels(width, height):
@@ -252,15 +297,11 @@ def compress_mipchain(fmt, rgba, width, height, params=None):
 def compress_batch_mips(fmt, textures, params=None, n_gpus=1, outputs=None):
     """textures: list of (rgba uint8 array, width, height); each is encoded with its full mip chain on device t % n_gpus."""
     params = params or Params()
-    n = len(textures)
-    arrs = [_u8(t[0], "rgba") for t in textures]
-    if outputs is None:
-        outputs = [np.empty(load().txp_mipchain_compressed_size(int(fmt), t[1], t[2]), dtype=np.uint8) for t in textures]
-    vp, sz = ctypes.c_void_p, ctypes.c_size_t
-    ins = (vp * n)(*[a.ctypes.data for a in arrs])
-    ous = (vp * n)(*[o.ctypes.data for o in outputs])
-    ws = (sz * n)(*[t[1] for t in textures])
-    hs = (sz * n)(*[t[2] for t in textures])
+    size = lambda w, h: load().txp_mipchain_compressed_size(int(fmt), w, h)
+    for t, (_a, w, h) in enumerate(textures):
+        if int(w) <= 0 or int(h) <= 0:
+            raise ValueError(f"textures[{t}]: bad dimensions {w}x{h}")
+    n, _keep, outputs, ins, ous, ws, hs = _batch_args(textures, lambda w, h: 4 * w * h, size, outputs)
     cp = params._c()
     check(load().txp_compress_batch_mips(int(fmt), ins, ws, hs, n, ctypes.byref(cp), ous, n_gpus))
     return outputs

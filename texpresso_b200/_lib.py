@@ -11,9 +11,9 @@ SO_PATH = pathlib.Path(os.environ.get("TEXPRESSO_B200_LIB", HERE / "libtexpresso
 EXPORTS = [
     "txp_num_blocks", "txp_block_size", "txp_compressed_size", "txp_compress", "txp_compress_pixels", "txp_decompress",
     "txp_compress_block_masked", "txp_decompress_block", "txp_compress_blocks", "txp_decompress_blocks",
-    "txp_compress_device", "txp_decompress_device", "txp_shard_rows", "txp_compress_multi", "txp_compress_batch",
+    "txp_compress_device", "txp_decompress_device", "txp_shard_rows", "txp_compress_multi", "txp_compress_batch", "txp_decompress_multi", "txp_decompress_batch",
     "txp_mip_levels", "txp_mipchain_compressed_size", "txp_compress_mipchain", "txp_compress_batch_mips",
-    "txp_device_count", "txp_set_device", "txp_last_error", "txp_kernel_launches", "txp_version", "txp_debug_set",
+    "txp_device_count", "txp_set_device", "txp_last_error", "txp_kernel_launches", "txp_version", "txp_debug_set", "txp_debug_get", "txp_measure_fp32_issue",
 ]
 
 
@@ -56,6 +56,8 @@ def load():
         "txp_shard_rows": (None, [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]),
         "txp_compress_multi": (ci, [ci, vp, sz, sz, sz, pp, vp, sz, ci]),
         "txp_compress_batch": (ci, [ci, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, pp, ctypes.POINTER(vp), ci]),
+        "txp_decompress_multi": (ci, [ci, vp, sz, sz, sz, vp, sz, ci]),
+        "txp_decompress_batch": (ci, [ci, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, ctypes.POINTER(vp), ci]),
         "txp_mip_levels": (ci, [sz, sz]),
         "txp_mipchain_compressed_size": (sz, [ci, sz, sz]),
         "txp_compress_mipchain": (ci, [ci, vp, sz, sz, sz, pp, vp, sz]),
@@ -66,6 +68,8 @@ def load():
         "txp_kernel_launches": (ctypes.c_uint64, []),
         "txp_version": (ctypes.c_char_p, []),
         "txp_debug_set": (ci, [ci, ci]),
+        "txp_debug_get": (ci, [ci, ctypes.POINTER(ctypes.c_uint64)]),
+        "txp_measure_fp32_issue": (ci, [ctypes.POINTER(ctypes.c_double)]),
     }
     for name in EXPORTS:
         fn = getattr(L, name)          # AttributeError if the library does not export it

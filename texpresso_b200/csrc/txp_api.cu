@@ -81,13 +81,14 @@ __global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour
 template <int FMT>
 __global__ void __launch_bounds__(COLOUR_WARPS * 32, TXP_COLOUR_MIN_CTAS) colour_search_kernel(const BlockSource src, const EncodeParams prm,
                                                                                                const uint4* __restrict__ setup,
-                                                                                               uint8_t* __restrict__ out) {
+                                                                                               uint8_t* __restrict__ out, const uint64_t first, const uint32_t n) {
     extern __shared__ __align__(16) unsigned char smem[];
     WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t b = (uint64_t)blockIdx.x * COLOUR_WARPS + warp;
-    if (b >= src.nblocks) return;
-    const uint4 su = __ldg(setup + b);
+    const uint64_t lb = (uint64_t)blockIdx.x * COLOUR_WARPS + warp;      // launch-local: blocks [first, first + n) of src
+    if (lb >= n) return;
+    const uint64_t b = first + lb;
+    const uint4 su = __ldg(setup + lb);
     if (!(su.z & SETUP_SEARCH)) return;                   // finished by the setup kernel (0 or 1 points)
     uint32_t pix = 0;
     bool valid = false;
@@ -151,21 +152,57 @@ __global__ void __launch_bounds__(256) expand_pixels_kernel(const uint8_t* __res
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Measurement helper (txp_measure_fp32_issue): 16 independent chains of rounded fp32 products per thread, 8 x unrolled.
+// With FMA contraction forbidden every fp32 operation of the ClusterFit search is one lane-instruction, so the rate of
+// this loop is the roof the search kernels are quoted against (bench.py roofline.peak_measured).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 6) fp32_issue_kernel(float* __restrict__ out, const float a, const int iters) {
+    float s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = threadIdx.x * 0.001f + i;
+    const float ra = a + threadIdx.x * 1e-9f;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s[i] = __fmul_rn(s[i], ra);
+        }
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc = __fadd_rn(acc, s[i]);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host runtime
 // ---------------------------------------------------------------------------------------------------
 static thread_local std::string t_last_error;
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_path_lane{0}, g_path_lane_iter{0}, g_path_warp{0}, g_path_hybrid{0};   // ClusterFit launches by kernel structure (txp_debug_get)
 // ClusterFit kernel structure (tuning knob, txp_debug_set(0, v) or TXP_COLOUR_VARIANT=auto|fused|warp|lane):
 //  0 auto  : setup kernel + lane-per-block search (txp_cluster_lane.cuh) for launches of at least g_lane_min_blocks
 //            blocks, setup kernel + warp-per-block search otherwise (few blocks: the warp kernel has 32x the parallelism)
 //  1 fused : the original single warp-per-block kernel          2 warp : always setup + warp-per-block search
 //  3 lane  : setup + lane-per-block search for every launch
+//  4 hybrid: full lane rounds + warp-per-block tail from one round upwards (A/B)
 static std::atomic<int> g_colour_variant{[] {
     const char* v = getenv("TXP_COLOUR_VARIANT");
     const std::string s = v ? v : "";
     return s == "fused" ? 1 : s == "warp" ? 2 : s == "lane" ? 3 : 0;
 }()};
 static std::atomic<long long> g_lane_min_blocks{[] { const char* v = getenv("TXP_LANE_MIN_BLOCKS"); return v ? atoll(v) : 262144ll; }()};
+// hybrid launches (launch_encode): a last lane round less than this many percent full takes the warp-per-block search; 0 = off
+// Measured (profiles/size_sweep_r02.jsonl): NOT a win.  A partly filled last round is not a whole round of time -- with fewer
+// warps per SM each lane gets a larger share of the FMA pipe, the lane kernel's time is linear in the block count above one
+// round -- so the default is 0 (off); variant 4 / key 2 keep the structure measurable.
+#ifndef TXP_TAIL_FRAC
+#define TXP_TAIL_FRAC 0
+#endif
+static std::atomic<int> g_chunk_mib{[] { const char* v = getenv("TXP_CHUNK_MIB"); return v ? atoi(v) : 0; }()};   // > 0: pipeline chunk size override (A/B)
+static std::atomic<int> g_plan_growth{[] { const char* v = getenv("TXP_PLAN_GROWTH"); return v ? atoi(v) : 3; }()};   // geometric chunk plan of small ClusterFit shards; <= 1: off
+static std::atomic<int> g_hybrid_tail{[] { const char* v = getenv("TXP_HYBRID_TAIL"); return v ? atoi(v) : TXP_TAIL_FRAC; }()};
 constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (292 B of scratch per block)
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
@@ -191,6 +228,7 @@ constexpr int MAX_DEVICES = 64;
 constexpr int NSLOTS = TXP_NSLOTS;   // pipeline slots (stream + staging) per device
 constexpr size_t CHUNK_BYTES = 32u << 20;       // largest input chunk per pipeline stage
 constexpr size_t MIN_CHUNK_BYTES = 2u << 20;    // smallest chunk worth a separate launch + copy
+constexpr size_t LANE_CHUNK_BYTES_MAX = 64u << 20;   // largest chunk taken so that a ClusterFit launch reaches the lane-per-block threshold
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -339,6 +377,89 @@ static EncodeParams to_device_params(const txp_params* p) {
     return e;
 }
 
+// blocks one round of the lane-per-block search holds: every SM runs TXP_LANE_MIN_CTAS CTAs of LANE_THREADS lanes, one block per lane
+static uint64_t lane_wave_blocks(const DeviceCtx& ctx) { return (uint64_t)ctx.sm_count * TXP_LANE_MIN_CTAS * LANE_THREADS; }
+
+// ClusterFit / IterativeClusterFit on blocks [first, first + n) of src, lane-per-block search:
+// K1 (thread per block; also emits the points of every colour set and a window-sorted permutation) -> K2L (lane per block)
+static int launch_cluster_lane(DeviceCtx& ctx, int format, const BlockSource& src, const EncodeParams& e, uint8_t* d_out, cudaStream_t st,
+                               const uint64_t first_block, const uint64_t nblocks) {
+    // at most LANE_CHUNK_BLOCKS blocks per launch pair (292 B of scratch per block), split evenly so that no launch is small
+    const uint64_t n_chunks = (nblocks + LANE_CHUNK_BLOCKS - 1) / LANE_CHUNK_BLOCKS;
+    const uint64_t chunk_blocks = ((nblocks + n_chunks - 1) / n_chunks + SETUP_WINDOW - 1) / SETUP_WINDOW * SETUP_WINDOW;
+    for (uint64_t off = 0; off < nblocks; off += chunk_blocks) {
+        const uint64_t first = first_block + off;
+        const uint32_t n = (uint32_t)std::min<uint64_t>(chunk_blocks, nblocks - off);
+        const size_t n32 = ((size_t)n + 31) & ~size_t(31);
+        const size_t pt_bytes = n32 * 16 * sizeof(float4), setup_bytes = n32 * sizeof(uint4), remap_bytes = n32 * sizeof(uint2);
+        const size_t word_bytes = n32 * sizeof(uint32_t);
+        uint8_t* scratch = nullptr;
+        TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), pt_bytes + setup_bytes + remap_bytes + 2 * word_bytes + 256, ctx.pool, st));
+        float4* pt = reinterpret_cast<float4*>(scratch);
+        uint4* setup = reinterpret_cast<uint4*>(scratch + pt_bytes);
+        uint2* remap = reinterpret_cast<uint2*>(scratch + pt_bytes + setup_bytes);
+        uint32_t* perm = reinterpret_cast<uint32_t*>(scratch + pt_bytes + setup_bytes + remap_bytes);
+        uint32_t* carry = perm + n32;
+        uint32_t* counters = carry + n32;
+        const unsigned g1 = (unsigned)((n + SETUP_WINDOW - 1) / SETUP_WINDOW), g2 = (unsigned)((n + LANE_THREADS - 1) / LANE_THREADS);
+        if (format == BC1) cluster_setup_sorted_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
+        else if (format == BC2) cluster_setup_sorted_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
+        else cluster_setup_sorted_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
+        cudaError_t aux_err = cudaSuccess;
+        if (e.algorithm == CLUSTER_FIT) {
+            if (format == BC1) cluster_lane_kernel<BC1><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
+            else if (format == BC2) cluster_lane_kernel<BC2><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
+            else cluster_lane_kernel<BC3><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            g_path_lane.fetch_add(1, std::memory_order_relaxed);
+        } else {
+            g_path_lane_iter.fetch_add(1, std::memory_order_relaxed);
+            // IterativeClusterFit: persistent warps draw blocks from a counter; BC1 = compress3 launch + compress4 launch
+            aux_err = cudaMemsetAsync(counters, 0, 256, st);
+            const unsigned cap = (unsigned)ctx.sm_count * TXP_LANE_ITER_MIN_CTAS, g3 = g2 < cap ? g2 : cap;
+            if (format == BC1) {
+                cluster_lane_iter_kernel<BC1, true><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+                cluster_lane_iter_kernel<BC1, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters + 1, first, n);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            } else if (format == BC2) {
+                cluster_lane_iter_kernel<BC2, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+            } else {
+                cluster_lane_iter_kernel<BC3, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+            }
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+        }
+        const cudaError_t launch_err = cudaGetLastError();
+        const cudaError_t free_err = cudaFreeAsync(scratch, st);    // stream-ordered: released after the search kernel
+        if (aux_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit memset: ") + cudaGetErrorString(aux_err));
+        if (launch_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit launch: ") + cudaGetErrorString(launch_err));
+        TXP_CUDA(free_err);
+    }
+    return TXP_OK;
+}
+
+// ... warp-per-block search: K1 (thread per block: alpha half, colour set, principal axis, first ordering) -> K2 (warp per block)
+static int launch_cluster_warp(DeviceCtx& ctx, int format, const BlockSource& src, const EncodeParams& e, uint8_t* d_out, cudaStream_t st,
+                               const uint64_t first, const uint64_t nblocks) {
+    const uint32_t n = (uint32_t)nblocks;
+    const unsigned grid = (unsigned)((nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS), threads = COLOUR_WARPS * 32;
+    uint4* setup = nullptr;
+    TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&setup), (size_t)nblocks * sizeof(uint4), ctx.pool, st));
+    const unsigned g1 = (unsigned)((nblocks + 127) / 128);
+    if (format == BC1) cluster_setup_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, first, n);
+    else if (format == BC2) cluster_setup_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, first, n);
+    else cluster_setup_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, first, n);
+    if (format == BC1) colour_search_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out, first, n);
+    else if (format == BC2) colour_search_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out, first, n);
+    else colour_search_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out, first, n);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    g_path_warp.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t launch_err = cudaGetLastError();
+    const cudaError_t free_err = cudaFreeAsync(setup, st);      // stream-ordered: released after the search kernel
+    if (launch_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit launch: ") + cudaGetErrorString(launch_err));
+    TXP_CUDA(free_err);
+    return TXP_OK;
+}
+
 // ---- kernel launchers -------------------------------------------------------------------------------
 // concurrent: the caller keeps several launches in flight on different streams (texture batches), so a launch does not
 // have to fill the GPU on its own for the lane-per-block kernels to pay off
@@ -395,85 +516,36 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         else if (format == BC2) range_encode_kernel<BC2><<<grid, 128, 0, st>>>(src, e, d_out);
         else range_encode_kernel<BC3><<<grid, 128, 0, st>>>(src, e, d_out);
     } else {
-        const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS);
-        const unsigned threads = COLOUR_WARPS * 32;
         const int variant = g_colour_variant.load(std::memory_order_relaxed);
-        // IterativeClusterFit: a block is 3-6 searches back to back on one lane, so a launch has to be larger still before the
-        // lane structure wins (8192^2 over 8 GPUs = 524 288 blocks per rank: 9.14 ms lane, 9.07 ms warp; 54.1 vs 66.7 ms at 4 Mi blocks)
-        const uint64_t lane_min = (uint64_t)g_lane_min_blocks.load(std::memory_order_relaxed) * (e.algorithm == ITERATIVE_CLUSTER_FIT ? 3 : 1) /
-                                  (concurrent ? 8 : 1);
-        const bool lane = variant == 3 || (variant == 0 && src.nblocks >= lane_min);
-        if (lane) {
-            // K1 (thread per block; also emits the points of every colour set and a window-sorted permutation) ->
-            // K2L (lane per block: search), in chunks of LANE_CHUNK_BLOCKS blocks
-            for (uint64_t first = 0; first < src.nblocks; first += LANE_CHUNK_BLOCKS) {
-                const uint32_t n = (uint32_t)std::min<uint64_t>(LANE_CHUNK_BLOCKS, src.nblocks - first);
-                const size_t n32 = ((size_t)n + 31) & ~size_t(31);
-                const size_t pt_bytes = n32 * 16 * sizeof(float4), setup_bytes = n32 * sizeof(uint4), remap_bytes = n32 * sizeof(uint2);
-                const size_t word_bytes = n32 * sizeof(uint32_t);
-                uint8_t* scratch = nullptr;
-                TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), pt_bytes + setup_bytes + remap_bytes + 2 * word_bytes + 256, ctx.pool, st));
-                float4* pt = reinterpret_cast<float4*>(scratch);
-                uint4* setup = reinterpret_cast<uint4*>(scratch + pt_bytes);
-                uint2* remap = reinterpret_cast<uint2*>(scratch + pt_bytes + setup_bytes);
-                uint32_t* perm = reinterpret_cast<uint32_t*>(scratch + pt_bytes + setup_bytes + remap_bytes);
-                uint32_t* carry = perm + n32;
-                uint32_t* counters = carry + n32;
-                const unsigned g1 = (unsigned)((n + SETUP_WINDOW - 1) / SETUP_WINDOW), g2 = (unsigned)((n + LANE_THREADS - 1) / LANE_THREADS);
-                if (format == BC1) cluster_setup_sorted_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
-                else if (format == BC2) cluster_setup_sorted_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
-                else cluster_setup_sorted_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
-                cudaError_t aux_err = cudaSuccess;
-                if (e.algorithm == CLUSTER_FIT) {
-                    if (format == BC1) cluster_lane_kernel<BC1><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
-                    else if (format == BC2) cluster_lane_kernel<BC2><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
-                    else cluster_lane_kernel<BC3><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
-                    g_launches.fetch_add(2, std::memory_order_relaxed);
-                } else {
-                    // IterativeClusterFit: persistent warps draw blocks from a counter; BC1 = compress3 launch + compress4 launch
-                    aux_err = cudaMemsetAsync(counters, 0, 256, st);
-                    const unsigned cap = (unsigned)ctx.sm_count * TXP_LANE_ITER_MIN_CTAS, g3 = g2 < cap ? g2 : cap;
-                    if (format == BC1) {
-                        cluster_lane_iter_kernel<BC1, true><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
-                        cluster_lane_iter_kernel<BC1, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters + 1, first, n);
-                        g_launches.fetch_add(1, std::memory_order_relaxed);
-                    } else if (format == BC2) {
-                        cluster_lane_iter_kernel<BC2, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
-                    } else {
-                        cluster_lane_iter_kernel<BC3, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
-                    }
-                    g_launches.fetch_add(2, std::memory_order_relaxed);
-                }
-                const cudaError_t launch_err = cudaGetLastError();
-                const cudaError_t free_err = cudaFreeAsync(scratch, st);    // stream-ordered: released after the search kernel
-                if (aux_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit memset: ") + cudaGetErrorString(aux_err));
-                if (launch_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit launch: ") + cudaGetErrorString(launch_err));
-                TXP_CUDA(free_err);
-            }
-            return TXP_OK;
-        }
         if (variant == 1) {                                                                        // single-kernel variant kept for A/B measurements
+            const unsigned grid = (unsigned)((src.nblocks + COLOUR_WARPS - 1) / COLOUR_WARPS), threads = COLOUR_WARPS * 32;
             if (format == BC1) colour_encode_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
             else if (format == BC2) colour_encode_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
             else colour_encode_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, d_out);
-        } else {
-            // K1 (thread per block: alpha half, colour set, principal axis, first ordering) -> K2 (warp per block: search)
-            uint4* setup = nullptr;
-            TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&setup), (size_t)src.nblocks * sizeof(uint4), ctx.pool, st));
-            const unsigned g1 = (unsigned)((src.nblocks + 127) / 128);
-            const uint32_t n = (uint32_t)src.nblocks;
-            if (format == BC1) cluster_setup_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, 0, n);
-            else if (format == BC2) cluster_setup_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, 0, n);
-            else cluster_setup_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, 0, n);
-            if (format == BC1) colour_search_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
-            else if (format == BC2) colour_search_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
-            else colour_search_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out);
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            const cudaError_t launch_err = cudaGetLastError();
-            const cudaError_t free_err = cudaFreeAsync(setup, st);      // stream-ordered: released after the search kernel
-            if (launch_err != cudaSuccess) return fail(TXP_ERR_CUDA, std::string("ClusterFit launch: ") + cudaGetErrorString(launch_err));
-            TXP_CUDA(free_err);
+            TXP_CUDA(cudaGetLastError());
+            return TXP_OK;
         }
+        // IterativeClusterFit: a block is 3-6 searches back to back on one lane, so a launch has to be larger still before the
+        // lane structure wins (8192^2 over 8 GPUs = 524 288 blocks per rank: 9.14 ms lane, 9.07 ms warp; 54.1 vs 66.7 ms at 4 Mi blocks)
+        const bool iterate = e.algorithm == ITERATIVE_CLUSTER_FIT;
+        const uint64_t lane_min = (uint64_t)g_lane_min_blocks.load(std::memory_order_relaxed) * (iterate ? 3 : 1) / (concurrent ? 8 : 1);
+        const uint64_t wave = lane_wave_blocks(ctx);
+        uint64_t n_lane = 0;                                     // blocks [0, n_lane) -> lane-per-block search, the rest -> warp-per-block search
+        if (variant == 3 || (variant == 0 && src.nblocks >= lane_min)) n_lane = src.nblocks;
+        if (variant == 4 && src.nblocks >= wave) n_lane = src.nblocks;
+        // Hybrid launch: one lane evaluates its block's 967 candidates back to back (0.2 ms), so a lane launch costs whole rounds of
+        // `wave` blocks.  A last round that is less than TXP_TAIL_FRAC full goes to the warp-per-block search instead, which spreads
+        // those blocks over the whole GPU at ~1.2-1.4x the work per block.
+        if (n_lane && !iterate && !concurrent && (variant == 0 || variant == 4) && g_hybrid_tail.load(std::memory_order_relaxed)) {
+            const uint64_t full = (src.nblocks / wave) * wave / SETUP_WINDOW * SETUP_WINDOW, tail = src.nblocks - full;
+            if (full > 0 && tail > 0 && tail * 100 < wave * (uint64_t)g_hybrid_tail.load(std::memory_order_relaxed)) n_lane = full;
+        }
+        int rc;
+        if (n_lane && (rc = launch_cluster_lane(ctx, format, src, e, d_out, st, 0, n_lane)) != TXP_OK) return rc;
+        if (n_lane < src.nblocks && (rc = launch_cluster_warp(ctx, format, src, e, d_out, st, n_lane, src.nblocks - n_lane)) != TXP_OK) return rc;
+        if (n_lane && n_lane < src.nblocks) g_path_hybrid.fetch_add(1, std::memory_order_relaxed);
+        return TXP_OK;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     TXP_CUDA(cudaGetLastError());
@@ -523,6 +595,76 @@ static int slot_wait(Slot& s) {
     return TXP_OK;
 }
 
+// CUDA call inside a pipeline loop: record the failure and leave the loop, so that the slots are always drained
+#define TXP_CUDA_BREAK(expr)                                                                    \
+    {                                                                                           \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) { rc = fail(TXP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); break; } \
+    }
+
+// after a failed pipeline: wait for everything in flight and forget the deferred copies into the caller's buffer
+static void slots_abandon(DeviceCtx& c) {
+    for (Slot& s : c.slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        s.user_out = nullptr; s.user_out_bytes = 0; s.busy = false;
+    }
+    cudaGetLastError();
+}
+
+// Rows per pipeline chunk for block rows [row0,row1) of a w-wide image.
+//  * at least ~6 chunks per call so that H2D, kernels and D2H of neighbouring chunks overlap (small shards at 8 ranks)
+//  * ClusterFit searches are compute-bound (>= 1 ms per 16 MiB against 0.3 ms of H2D) and their lane-per-block kernels want
+//    launches of at least lane_min blocks (3 x that for IterativeClusterFit, see launch_encode): a shard that holds two or
+//    more such launches is cut into chunks of that many blocks, rounded UP to whole block rows
+static size_t pipeline_rows_per_chunk(int format, const txp_params* p, size_t w, size_t rows) {
+    const size_t bw = (w + 3) / 4, row_bytes = 16 * w;
+    size_t chunk_bytes = rows * row_bytes / 6;
+    if (chunk_bytes > CHUNK_BYTES) chunk_bytes = CHUNK_BYTES;
+    if (chunk_bytes < MIN_CHUNK_BYTES) chunk_bytes = MIN_CHUNK_BYTES;
+    size_t rows_per_chunk = chunk_bytes / row_bytes;
+    if (format <= BC3 && p->algorithm != RANGE_FIT) {
+        const long long lm = g_lane_min_blocks.load(std::memory_order_relaxed);
+        const size_t lane_blocks = (size_t)(lm > 0 ? lm : 1) * (p->algorithm == ITERATIVE_CLUSTER_FIT ? 3 : 1);
+        const size_t lane_rows = (lane_blocks + bw - 1) / bw;                      // ceil: the launch must not fall below the threshold
+        if (lane_rows * row_bytes <= LANE_CHUNK_BYTES_MAX && rows >= 2 * lane_rows && rows_per_chunk < lane_rows) rows_per_chunk = lane_rows;
+    }
+    const int force_mib = g_chunk_mib.load(std::memory_order_relaxed);
+    if (force_mib > 0) rows_per_chunk = ((size_t)force_mib << 20) / row_bytes;
+    return rows_per_chunk ? rows_per_chunk : 1;
+}
+
+// Chunk sizes (block rows) of the H2D -> kernels -> D2H pipeline for a shard of `rows` block rows.
+//  * default: uniform chunks, the first one quarter-sized (its H2D copy is the only one nothing overlaps); for ClusterFit the rows
+//    after it are spread evenly, so that no short last chunk falls below the lane-per-block threshold
+//  * ClusterFit shards of fewer than three lane-sized chunks (8192^2 over 8 GPUs: 256 block rows per rank): geometric growth
+//    c, G c, rest -- every chunk's kernels cover the next chunk's copy (compute : PCIe time is ~3.6 : 1 for ClusterFit, ~10 : 1
+//    for IterativeClusterFit) and only a small copy is exposed at either end
+static std::vector<size_t> pipeline_plan(int format, const txp_params* p, size_t w, size_t rows) {
+    const size_t bw = (w + 3) / 4;
+    size_t rows_per_chunk = pipeline_rows_per_chunk(format, p, w, rows);
+    std::vector<size_t> plan;
+    const bool cluster = format <= BC3 && p->algorithm != RANGE_FIT;
+    const int growth = g_plan_growth.load(std::memory_order_relaxed);
+    if (cluster && growth > 1 && g_chunk_mib.load(std::memory_order_relaxed) == 0 && rows < 3 * rows_per_chunk && rows * bw >= 131072) {
+        const size_t G = (size_t)growth * (p->algorithm == ITERATIVE_CLUSTER_FIT ? 2 : 1);
+        const size_t min_rows = (16384 + bw - 1) / bw;                       // a launch of at least 16 Ki blocks
+        size_t c1 = (rows + G * G + G) / (1 + G + G * G);
+        if (c1 < min_rows) c1 = min_rows;
+        size_t c2 = G * c1;
+        if (c1 + c2 + c2 / 2 > rows) { plan.push_back(c1); plan.push_back(rows - c1); return plan; }
+        plan.push_back(c1); plan.push_back(c2); plan.push_back(rows - c1 - c2);
+        return plan;
+    }
+    const size_t first_rows = (TXP_SMALL_FIRST_CHUNK && rows >= 3 * rows_per_chunk && rows_per_chunk >= 4) ? rows_per_chunk / 4 : rows_per_chunk;
+    if (cluster && rows > first_rows) {
+        const size_t rest = rows - first_rows, n = rest / rows_per_chunk;
+        if (n >= 1) rows_per_chunk = (rest + n - 1) / n;
+    }
+    plan.push_back(first_rows);
+    plan.push_back(rows_per_chunk);
+    return plan;
+}
+
 // Encode block rows [row0,row1) (clipped to nblocks_total) of an image held in HOST memory on the
 // current device.  `out` points at the first byte of block row `row0`.
 // layout: TXP_PIXELS_RGBA8 = as the reference takes it; the other layouts are expanded on the device.
@@ -532,25 +674,13 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
     const size_t bpp = layout_bpp(layout);
     const size_t bs = (size_t)block_bytes(format), bw = (w + 3) / 4;
     const bool in_direct = dma_direct(rgba), out_direct = dma_direct(out);
-    // at least ~6 chunks per call so that H2D, kernels and D2H of neighbouring chunks overlap (small shards at 8 ranks)
-    size_t chunk_bytes = (row1 - row0) * 16 * w / 6;
-    if (chunk_bytes > CHUNK_BYTES) chunk_bytes = CHUNK_BYTES;
-    if (chunk_bytes < MIN_CHUNK_BYTES) chunk_bytes = MIN_CHUNK_BYTES;
-    // ClusterFit searches are compute-bound (>= 1 ms per 16 MiB against 0.3 ms of H2D) and their lane-per-block kernels want
-    // launches of at least g_lane_min_blocks blocks: a shard that holds two or more such launches is not cut any finer
-    if (format <= BC3 && p->algorithm != RANGE_FIT) {
-        const size_t lane_bytes = (size_t)g_lane_min_blocks.load(std::memory_order_relaxed) * 64;
-        if (chunk_bytes < lane_bytes && lane_bytes <= CHUNK_BYTES && (row1 - row0) * 16 * w >= 2 * lane_bytes) chunk_bytes = lane_bytes;
-    }
-    size_t rows_per_chunk = chunk_bytes / (16 * w);
-    if (rows_per_chunk == 0) rows_per_chunk = 1;
+    const std::vector<size_t> plan = pipeline_plan(format, p, w, row1 - row0);
+    const size_t rows_per_chunk = plan.size() > 1 ? plan[1] : plan[0];
     int rc = TXP_OK;
     size_t chunk = 0;
     uint64_t blocks_left = blocks_in_range;
-    // the first chunk's H2D copy is the one nothing overlaps: when there are several chunks, start with a quarter-sized one
-    const size_t first_rows = (TXP_SMALL_FIRST_CHUNK && (row1 - row0) >= 3 * rows_per_chunk && rows_per_chunk >= 4) ? rows_per_chunk / 4 : rows_per_chunk;
-    size_t step = first_rows;
-    for (size_t r = row0; r < row1 && blocks_left > 0 && rc == TXP_OK; r += step, step = rows_per_chunk, ++chunk) {
+    size_t step = plan[0];
+    for (size_t r = row0; r < row1 && blocks_left > 0 && rc == TXP_OK; r += step, ++chunk, step = std::max<size_t>(1, plan[chunk < plan.size() ? chunk : plan.size() - 1])) {
         const size_t r_end = (r + step < row1) ? r + step : row1;
         uint64_t nblk = (uint64_t)(r_end - r) * bw;
         if (nblk > blocks_left) nblk = blocks_left;
@@ -571,7 +701,7 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
                 std::memcpy(s.h_in, src_ptr, in_bytes);
                 src_ptr = s.h_in;
             }
-            TXP_CUDA(cudaMemcpyAsync(bpp == 4 ? s.d_in : s.d_raw, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
+            TXP_CUDA_BREAK(cudaMemcpyAsync(bpp == 4 ? s.d_in : s.d_raw, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
             if (bpp != 4) {
                 const size_t npix = h_sub * w;
                 const unsigned g = (unsigned)((npix + 255) / 256);
@@ -581,24 +711,83 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
                 else if (layout == TXP_PIXELS_RG8) expand_pixels_kernel<TXP_PIXELS_RG8><<<g, 256, 0, s.stream>>>(s.d_raw, d32, npix);
                 else expand_pixels_kernel<TXP_PIXELS_RGB8><<<g, 256, 0, s.stream>>>(s.d_raw, d32, npix);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
-                TXP_CUDA(cudaGetLastError());
+                TXP_CUDA_BREAK(cudaGetLastError());
             }
         }
         const BlockSource bsrc = image_source(s.d_in, w, h_sub, nblk);
         if ((rc = launch_encode(c, format, bsrc, p, s.d_out, s.stream, TXP_HOST_CONCURRENT != 0 && (row1 - row0) > 2 * rows_per_chunk)) != TXP_OK) break;
         uint8_t* dst = out + (r - row0) * bw * bs;
         if (out_direct) {
-            TXP_CUDA(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
+            TXP_CUDA_BREAK(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
         } else {
             if ((rc = grow_pinned(&s.h_out, &s.h_out_cap, out_bytes)) != TXP_OK) break;
-            TXP_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+            TXP_CUDA_BREAK(cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
             s.user_out = dst; s.user_out_bytes = out_bytes;
         }
-        TXP_CUDA(cudaEventRecord(s.done, s.stream));
+        TXP_CUDA_BREAK(cudaEventRecord(s.done, s.stream));
         s.busy = true;
     }
+    if (rc != TXP_OK) { const std::string keep = t_last_error; slots_abandon(c); t_last_error = keep; return rc; }
     for (Slot& s : c.slots) { const int r2 = slot_wait(s); if (rc == TXP_OK) rc = r2; }
     return rc;
+}
+
+// Decode block rows [row0,row1) of a w x h image on the current device.  `data` points at the first block of block row
+// row0, `out` at pixel row 4*row0 (reference grain: one block row per rayon task, lib.rs:128-134).  Chunks of block rows are
+// pipelined through the slots: the small H2D copy and the kernel of one chunk overlap the 8x larger D2H copy of the previous one.
+static int decompress_host_rows(DeviceCtx& c, int format, const uint8_t* data, size_t w, size_t h, uint8_t* out, size_t row0, size_t row1) {
+    const size_t bs = (size_t)block_bytes(format), bw = (w + 3) / 4;
+    const bool in_direct = dma_direct(data), out_direct = dma_direct(out);
+    size_t chunk_bytes = (row1 - row0) * 16 * w / 6;                 // bytes of decoded pixels per chunk
+    if (chunk_bytes > CHUNK_BYTES) chunk_bytes = CHUNK_BYTES;
+    if (chunk_bytes < MIN_CHUNK_BYTES) chunk_bytes = MIN_CHUNK_BYTES;
+    size_t rows_per_chunk = chunk_bytes / (16 * w);
+    if (rows_per_chunk == 0) rows_per_chunk = 1;
+    int rc = TXP_OK;
+    size_t chunk = 0;
+    for (size_t r = row0; r < row1 && rc == TXP_OK; r += rows_per_chunk, ++chunk) {
+        const size_t r_end = (r + rows_per_chunk < row1) ? r + rows_per_chunk : row1;
+        const size_t y0 = 4 * r, y1 = (4 * r_end < h) ? 4 * r_end : h;
+        if (y1 <= y0) break;
+        const size_t h_sub = y1 - y0;
+        const uint64_t nblk = (uint64_t)(r_end - r) * bw;
+        const size_t in_bytes = (size_t)nblk * bs, out_bytes = h_sub * w * 4;
+        Slot& s = c.slots[chunk % NSLOTS];
+        if ((rc = slot_wait(s)) != TXP_OK) break;
+        if ((rc = grow_dev(&s.d_in, &s.d_in_cap, in_bytes)) != TXP_OK) break;
+        if ((rc = grow_dev(&s.d_out, &s.d_out_cap, out_bytes)) != TXP_OK) break;
+        const uint8_t* src_ptr = data + (r - row0) * bw * bs;
+        if (!in_direct) {
+            if ((rc = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) break;
+            std::memcpy(s.h_in, src_ptr, in_bytes);
+            src_ptr = s.h_in;
+        }
+        TXP_CUDA_BREAK(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
+        if ((rc = launch_decode(format, s.d_in, nblk, (uint32_t)w, (uint32_t)h_sub, (uint32_t)bw, s.d_out, s.stream)) != TXP_OK) break;
+        uint8_t* dst = out + (y0 - 4 * row0) * w * 4;
+        if (out_direct) {
+            TXP_CUDA_BREAK(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
+        } else {
+            if ((rc = grow_pinned(&s.h_out, &s.h_out_cap, out_bytes)) != TXP_OK) break;
+            TXP_CUDA_BREAK(cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+            s.user_out = dst; s.user_out_bytes = out_bytes;
+        }
+        TXP_CUDA_BREAK(cudaEventRecord(s.done, s.stream));
+        s.busy = true;
+    }
+    if (rc != TXP_OK) { const std::string keep = t_last_error; slots_abandon(c); t_last_error = keep; return rc; }
+    for (Slot& s : c.slots) { const int r2 = slot_wait(s); if (rc == TXP_OK) rc = r2; }
+    return rc;
+}
+
+static int decompress_checked(int format, const uint8_t* data, size_t data_len, size_t width, size_t height, const uint8_t* output, size_t output_len) {
+    int rc;
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if ((rc = check_dims(width, height)) != TXP_OK) return rc;
+    if (!data || !output) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    if (data_len < txp_compressed_size(format, width, height)) return fail(TXP_ERR_BUFFER_TOO_SMALL, "data shorter than compressed_size (reference: slice panic, lib.rs:138)");
+    if (output_len < width * height * 4) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than 4*width*height");
+    return TXP_OK;
 }
 
 static int compress_checked(int format, const uint8_t* rgba, size_t rgba_len, size_t w, size_t h, const txp_params* p,
@@ -637,8 +826,8 @@ static int mip_layout(int format, size_t w, size_t h, BlockSource* src, size_t* 
 
 // enqueue H2D(level 0) -> mip kernels -> one encode launch -> D2H on slot s; the caller waits on the slot
 // with_mips = false: level 0 only (a whole texture per slot: txp_compress_batch)
-static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
-                            const bool concurrent = false, const bool with_mips = true) {
+static int mipchain_enqueue_impl(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
+                                 const bool concurrent, const bool with_mips) {
     BlockSource src;
     size_t total_px = 0, total_out = 0;
     int n = 1;
@@ -686,6 +875,19 @@ static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* 
     return TXP_OK;
 }
 
+// a failure after the first asynchronous operation must not leave work in flight on a slot that is not marked busy
+static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
+                            const bool concurrent = false, const bool with_mips = true) {
+    const int rc = mipchain_enqueue_impl(ctx, s, format, rgba, w, h, p, output, concurrent, with_mips);
+    if (rc != TXP_OK) {
+        const std::string keep = t_last_error;
+        cudaStreamSynchronize(s.stream); cudaGetLastError();
+        s.user_out = nullptr; s.user_out_bytes = 0; s.busy = false;
+        t_last_error = keep;
+    }
+    return rc;
+}
+
 }  // namespace txp
 
 using namespace txp;
@@ -708,9 +910,56 @@ uint64_t txp_kernel_launches(void) { return g_launches.load(); }
 const char* txp_version(void) { return "texpresso_b200 0.1 (sm_100a)"; }
 
 int txp_debug_set(int key, int value) {
-    if (key == 0) { if (value < 0 || value > 3) return fail(TXP_ERR_ARGUMENT, "colour variant must be 0..3"); g_colour_variant.store(value); return TXP_OK; }
-    if (key == 1) { g_lane_min_blocks.store(value); return TXP_OK; }
+    if (key == 0) { if (value < 0 || value > 4) return fail(TXP_ERR_ARGUMENT, "colour variant must be 0..4"); g_colour_variant.store(value); return TXP_OK; }
+    if (key == 4) { if (value < 0 || value > 16) return fail(TXP_ERR_ARGUMENT, "plan growth must be 0..16"); g_plan_growth.store(value); return TXP_OK; }
+    if (key == 3) { if (value < 0 || value > 4096) return fail(TXP_ERR_ARGUMENT, "chunk override must be 0..4096 MiB"); g_chunk_mib.store(value); return TXP_OK; }
+    if (key == 2) { if (value < 0 || value > 100) return fail(TXP_ERR_ARGUMENT, "hybrid tail threshold must be 0..100 (percent of a lane round)"); g_hybrid_tail.store(value); return TXP_OK; }
+    if (key == 1) { if (value < 1) return fail(TXP_ERR_ARGUMENT, "lane threshold must be >= 1 block"); g_lane_min_blocks.store(value); return TXP_OK; }
     return fail(TXP_ERR_ARGUMENT, "unknown debug key");
+}
+
+int txp_debug_get(int key, uint64_t* value) {
+    if (!value) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    switch (key) {
+    case 0: *value = (uint64_t)g_colour_variant.load(); return TXP_OK;
+    case 1: *value = (uint64_t)g_lane_min_blocks.load(); return TXP_OK;
+    case 2: *value = g_path_lane.load(); return TXP_OK;          // ClusterFit launches that took the lane-per-block search
+    case 3: *value = g_path_lane_iter.load(); return TXP_OK;     // IterativeClusterFit launches that took the lane-per-block search
+    case 4: *value = g_path_warp.load(); return TXP_OK;          // (Iterative)ClusterFit launches that took the warp-per-block search
+    case 5: *value = g_path_hybrid.load(); return TXP_OK;        // ClusterFit launches split into full lane rounds + a warp-per-block tail
+    case 6: *value = (uint64_t)g_hybrid_tail.load(); return TXP_OK;
+    default: return fail(TXP_ERR_ARGUMENT, "unknown debug key");
+    }
+}
+
+int txp_measure_fp32_issue(double* lane_ops_per_second) {
+    if (!lane_ops_per_second) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    DeviceCtx* c;
+    int rc;
+    if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    const int grid = c->sm_count * 6, iters = 2048;
+    float* d = nullptr;
+    TXP_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), (size_t)grid * 128 * sizeof(float)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaEventCreate(&e0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e1);
+    float best = 0.f;
+    for (int rep = 0; rep < 4 && err == cudaSuccess; ++rep) {              // rep 0 = warm-up
+        cudaEventRecord(e0, nullptr);
+        fp32_issue_kernel<<<grid, 128>>>(d, 1.0001f, iters);
+        cudaEventRecord(e1, nullptr);
+        err = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0.f && (best == 0.f || ms < best)) best = ms;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d);
+    if (err != cudaSuccess || best <= 0.f) return fail(TXP_ERR_CUDA, std::string("fp32 issue measurement: ") + cudaGetErrorString(err));
+    *lane_ops_per_second = (double)grid * 128.0 * iters * 128.0 / (best * 1e-3);
+    return TXP_OK;
 }
 
 int txp_device_count(void) {
@@ -800,25 +1049,17 @@ int txp_compress(int format, const uint8_t* rgba, size_t rgba_len, size_t width,
 int txp_decompress(int format, const uint8_t* data, size_t data_len, size_t width, size_t height, uint8_t* output,
                    size_t output_len) {
     int rc;
-    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
-    if ((rc = check_dims(width, height)) != TXP_OK) return rc;
-    if (!data || !output) return fail(TXP_ERR_ARGUMENT, "null pointer");
-    const size_t need_in = txp_compressed_size(format, width, height), need_out = width * height * 4;
-    if (data_len < need_in) return fail(TXP_ERR_BUFFER_TOO_SMALL, "data shorter than compressed_size (reference: slice panic, lib.rs:138)");
-    if (output_len < need_out) return fail(TXP_ERR_BUFFER_TOO_SMALL, "output shorter than 4*width*height");
-    if (need_out == 0) return TXP_OK;
+    if ((rc = decompress_checked(format, data, data_len, width, height, output, output_len)) != TXP_OK) return rc;
+    if (width * height == 0) return TXP_OK;
     DeviceCtx* c;
     if ((rc = current_ctx(&c)) != TXP_OK) return rc;
+    if (is_device_ptr(data) && is_device_ptr(output)) {
+        if ((rc = txp_decompress_device(format, data, width, height, output, output_len, nullptr)) != TXP_OK) return rc;
+        TXP_CUDA(cudaStreamSynchronize(nullptr));
+        return TXP_OK;
+    }
     std::lock_guard<std::mutex> lk(c->mu);
-    Slot& s = c->slots[0];
-    if ((rc = grow_dev(&s.d_in, &s.d_in_cap, need_in)) != TXP_OK) return rc;
-    if ((rc = grow_dev(&s.d_out, &s.d_out_cap, need_out)) != TXP_OK) return rc;
-    TXP_CUDA(cudaMemcpyAsync(s.d_in, data, need_in, cudaMemcpyDefault, s.stream));
-    const uint64_t nblocks = (uint64_t)txp_num_blocks(width) * txp_num_blocks(height);
-    if ((rc = launch_decode(format, s.d_in, nblocks, (uint32_t)width, (uint32_t)height, (uint32_t)txp_num_blocks(width), s.d_out, s.stream)) != TXP_OK) return rc;
-    TXP_CUDA(cudaMemcpyAsync(output, s.d_out, need_out, cudaMemcpyDefault, s.stream));
-    TXP_CUDA(cudaStreamSynchronize(s.stream));
-    return TXP_OK;
+    return decompress_host_rows(*c, format, data, width, height, output, 0, txp_num_blocks(height));
 }
 
 int txp_compress_blocks(int format, const uint8_t* rgba_blocks, const uint32_t* masks, size_t n, const txp_params* params,
@@ -939,6 +1180,7 @@ int txp_compress_batch_mips(int format, const uint8_t* const* rgba, const size_t
                 size_t k = 0;                              // texture t -> device t % n_gpus, slots round-robin so that
                 for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus, ++k) {   // copies overlap kernels
                     Slot& s = c->slots[k % NSLOTS];
+                    if (!rgba[t] || !outputs[t]) { r = fail(TXP_ERR_ARGUMENT, "null texture pointer"); break; }
                     if ((r = slot_wait(s)) != TXP_OK) break;
                     r = mipchain_enqueue(*c, s, format, rgba[t], widths[t], heights[t], params, outputs[t], true);
                 }
@@ -1030,6 +1272,113 @@ int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* wid
                         r = compress_host_rows(*c, format, rgba[t], w, h, params, outputs[t], 0, rows, (uint64_t)bw * rows);
                     }
                 }
+                for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
+            }
+            rcs[(size_t)g] = r;
+            if (r != TXP_OK) errs[(size_t)g] = t_last_error;
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int g = 0; g < n_gpus; ++g)
+        if (rcs[(size_t)g] != TXP_OK) return fail(rcs[(size_t)g], "gpu " + std::to_string(g) + ": " + errs[(size_t)g]);
+    return TXP_OK;
+}
+
+int txp_decompress_multi(int format, const uint8_t* data, size_t data_len, size_t width, size_t height, uint8_t* output,
+                         size_t output_len, int n_gpus) {
+    int rc;
+    if ((rc = decompress_checked(format, data, data_len, width, height, output, output_len)) != TXP_OK) return rc;
+    const int ndev = txp_device_count();
+    if (ndev < 0) return ndev;
+    if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
+    if (width * height == 0) return TXP_OK;
+    const size_t bs = (size_t)block_bytes(format), bw = txp_num_blocks(width), rows = txp_num_blocks(height);
+    std::vector<int> rcs((size_t)n_gpus, TXP_OK);
+    std::vector<std::string> errs((size_t)n_gpus);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_gpus; ++g) {
+        workers.emplace_back([&, g]() {
+            const size_t r0 = rows * (size_t)g / (size_t)n_gpus, r1 = rows * (size_t)(g + 1) / (size_t)n_gpus;
+            if (r0 >= r1) return;
+            int r = TXP_OK;
+            DeviceCtx* c = nullptr;
+            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            if (r == TXP_OK) {
+                std::lock_guard<std::mutex> lk(c->mu);
+                r = decompress_host_rows(*c, format, data + r0 * bw * bs, width, height, output + 4 * r0 * width * 4, r0, r1);
+            }
+            rcs[(size_t)g] = r;
+            if (r != TXP_OK) errs[(size_t)g] = t_last_error;
+        });
+    }
+    for (auto& t : workers) t.join();
+    for (int g = 0; g < n_gpus; ++g)
+        if (rcs[(size_t)g] != TXP_OK) return fail(rcs[(size_t)g], "gpu " + std::to_string(g) + ": " + errs[(size_t)g]);
+    return TXP_OK;
+}
+
+int txp_decompress_batch(int format, const uint8_t* const* data, const size_t* widths, const size_t* heights, size_t n_textures,
+                         uint8_t* const* outputs, int n_gpus) {
+    if (format < 0 || format > 4) return fail(TXP_ERR_FORMAT, "format must be 0..4 (Bc1..Bc5)");
+    if (n_textures == 0) return TXP_OK;
+    if (!data || !widths || !heights || !outputs) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    const int ndev = txp_device_count();
+    if (ndev < 0) return ndev;
+    if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
+    std::vector<int> rcs((size_t)n_gpus, TXP_OK);
+    std::vector<std::string> errs((size_t)n_gpus);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_gpus; ++g) {
+        workers.emplace_back([&, g]() {
+            int r = TXP_OK;
+            DeviceCtx* c = nullptr;
+            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            if (r == TXP_OK) {
+                std::lock_guard<std::mutex> lk(c->mu);
+                size_t k = 0;
+                for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus) {
+                    const size_t w = widths[t], h = heights[t];
+                    if ((r = check_dims(w, h)) != TXP_OK) break;
+                    if (!data[t] || !outputs[t]) { r = fail(TXP_ERR_ARGUMENT, "null texture pointer"); break; }
+                    if (w * h == 0) continue;
+                    const size_t in_bytes = txp_compressed_size(format, w, h), out_bytes = w * h * 4;
+                    if (out_bytes <= CHUNK_BYTES) {
+                        // a whole texture per pipeline slot: copies and kernels of neighbouring textures overlap
+                        Slot& s = c->slots[k++ % NSLOTS];
+                        if ((r = slot_wait(s)) != TXP_OK) break;
+                        if ((r = grow_dev(&s.d_in, &s.d_in_cap, in_bytes)) != TXP_OK) break;
+                        if ((r = grow_dev(&s.d_out, &s.d_out_cap, out_bytes)) != TXP_OK) break;
+                        const uint8_t* src_ptr = data[t];
+                        if (!dma_direct(src_ptr)) {
+                            if ((r = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) break;
+                            std::memcpy(s.h_in, src_ptr, in_bytes);
+                            src_ptr = s.h_in;
+                        }
+                        int rc = TXP_OK;
+                        do {
+                            TXP_CUDA_BREAK(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
+                            if ((rc = launch_decode(format, s.d_in, (uint64_t)txp_num_blocks(w) * txp_num_blocks(h), (uint32_t)w, (uint32_t)h,
+                                                    (uint32_t)txp_num_blocks(w), s.d_out, s.stream)) != TXP_OK) break;
+                            if (dma_direct(outputs[t])) {
+                                TXP_CUDA_BREAK(cudaMemcpyAsync(outputs[t], s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
+                            } else {
+                                if ((rc = grow_pinned(&s.h_out, &s.h_out_cap, out_bytes)) != TXP_OK) break;
+                                TXP_CUDA_BREAK(cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+                                s.user_out = outputs[t]; s.user_out_bytes = out_bytes;
+                            }
+                            TXP_CUDA_BREAK(cudaEventRecord(s.done, s.stream));
+                            s.busy = true;
+                        } while (0);
+                        r = rc;
+                    } else {
+                        for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
+                        if (r != TXP_OK) break;
+                        r = decompress_host_rows(*c, format, data[t], w, h, outputs[t], 0, txp_num_blocks(h));
+                    }
+                }
+                if (r != TXP_OK) { const std::string keep = t_last_error; slots_abandon(*c); t_last_error = keep; }
                 for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
             }
             rcs[(size_t)g] = r;
