@@ -88,6 +88,26 @@ def test_images(fmt, size, kind):
 
 
 @pytest.mark.parametrize("fmt", [O.BC4, O.BC5])
+@pytest.mark.parametrize("size", [(128, 4), (128, 7), (256, 130), (1152, 515), (2048, 64), (4096, 1030)])
+@pytest.mark.parametrize("kind", ["r_rg", "smooth"])
+def test_images_tma_staged(fmt, size, kind):
+    """widths that are a multiple of 128 pixels take alpha_lattice_tma_kernel (one cp.async.bulk.tensor per 32-block strip):
+    ragged heights (partial bottom block row through the literal path), more tiles than resident warps, and an output that is
+    longer than needed (the extra block rows are encoded fully masked)."""
+    import texpresso_b200 as T
+    from texpresso_b200 import synth
+    w, h = size
+    img = np.ascontiguousarray(synth.generate(kind, w, (h + 3) // 4 * 4, seed=78)[:h])
+    got = T.Format(fmt).compress(img, w, h, T.Params())
+    assert np.array_equal(got, O.compress(fmt, img, w, h, threads=8))
+    bs = 8 if fmt == O.BC4 else 16
+    n = got.size + (w // 4) * bs + 5 * bs                      # one extra block row + a partial row
+    out = np.full(n, 0xEE, np.uint8)
+    T.Format(fmt).compress(img, w, h, T.Params(), output=out)
+    assert np.array_equal(out, O.compress(fmt, img, w, h, out_len=n))
+
+
+@pytest.mark.parametrize("fmt", [O.BC4, O.BC5])
 def test_narrow_and_flat_blocks(fmt):
     """closed-form path for flat / narrow-range blocks (alpha_fit_narrow): every lo, every range 0..6, plus flat 0 / 255,
     ranges clamped at 255 (lo > 248) and narrow ranges that touch 0 or 255 (those stay on the literal path)"""

@@ -320,7 +320,7 @@ def test_fullsize_8192_bc1_iterative_auto_path_vs_oracle(T):
     lane0, warp0 = _debug_get(3), _debug_get(4)
     a = T.Format.Bc1.compress(img, w, h, tp)
     lane, warp = _debug_get(3) - lane0, _debug_get(4) - warp0
-    assert lane >= 4 and warp <= 1, (lane, warp)             # 5-6 chunks of 384 block rows, the first one quarter-sized
+    assert lane >= 3 and warp <= 1, (lane, warp)             # a 64-row first chunk (warp kernels), then three chunks of ~83 MiB
     rowbytes = (w // 4) * 8
     for y0 in (0, 1024, 4096 + 512, h - 32):                  # first chunk, chunk interiors, last rows
         want = O.compress(0, img[y0:y0 + 32, :2048], 2048, 32, op, threads=8).reshape(8, -1)
@@ -342,12 +342,12 @@ def test_fullsize_8192_bc1_iterative_auto_path_vs_oracle(T):
 def test_lane_chunk_rows_round_up(T):
     """Widths for which 16 MiB is not a whole number of block rows still reach the lane-per-block kernels (chunk rows are rounded up)."""
     from texpresso_b200 import synth
-    w, h = 6000, 1600                                         # 1500 blocks per row: 174 rows would be 261 000 < 262 144
+    w, h = 6000, 2400                                         # 1500 blocks per row: 174 rows would be 261 000 < 262 144
     img = synth.generate("noise_opaque", w, h, seed=12)
     tp, op = _params(T, 1, O.PERCEPTUAL)
     lane0 = _debug_get(2)
     a = T.Format.Bc1.compress(img, w, h, tp)
-    assert _debug_get(2) - lane0 >= 2
+    assert _debug_get(2) - lane0 >= 3
     want = O.compress(0, img[800:832], w, 32, op, threads=8)
     assert np.array_equal(a[200 * 1500 * 8:208 * 1500 * 8], want)
 

@@ -472,7 +472,7 @@ constexpr size_t lattice_smem() { return 512 * sizeof(uint4) + (THREADS / 32) * 
 
 template <int FMT, int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_kernel(const __grid_constant__ BlockSource src, uint8_t* __restrict__ out, const uint32_t ntiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* tab = reinterpret_cast<uint4*>(smem_raw);
     WarpQueue* queues = reinterpret_cast<WarpQueue*>(tab + 512);
     for (int i = threadIdx.x; i < 512; i += THREADS) tab[i] = g_alpha_lattice[i];
@@ -520,7 +520,7 @@ constexpr size_t lattice_image_smem() { return 512 * sizeof(uint4) + (size_t)THR
 template <int FMT, int THREADS, int MIN_CTAS, int STAGES>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(const __grid_constant__ BlockSource src, uint8_t* __restrict__ out,
                                                                                const uint32_t ntiles, const uint32_t step_q, const uint32_t step_r) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* tab = reinterpret_cast<uint4*>(smem_raw);
     uint4* ring = tab + 512;                                                          // [warp][stage][row][lane]
     WarpQueue* queues = reinterpret_cast<WarpQueue*>(ring + THREADS * STAGES * 4);
@@ -579,6 +579,122 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_image_kernel(
         st = st + 1 == STAGES ? 0 : st + 1;
     }
     cp_async_wait<0>();
+    queue_flush<FMT>(q, qa, qb, lane, src, out, tab);
+}
+
+// ---- image-mode kernel with TMA staging --------------------------------------------------------------------------------
+// Same algorithm and per-warp ring as alpha_lattice_image_kernel, but a tile's strip -- 32 blocks = 128 pixels x 4 rows --
+// is ONE cp.async.bulk.tensor.2d issued by lane 0 (box {128 px, 4 rows} of a 2-D tensor map over the RGBA image, landing as
+// [row][lane] x 16 B: the layout the cp.async ring has), completion through one mbarrier per (warp, stage).  The other 31
+// lanes issue nothing for the copy and no lane computes global addresses.  Needs blocks-per-row % 32 == 0 (a tile never
+// straddles two block rows; w % 128 == 0: every power-of-two texture from 128 up); other widths take the cp.async kernel.
+// Rows past h (h % 4 != 0) are never staged: those tiles go to the literal path through the queue, as in the cp.async kernel.
+__device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const uint32_t bar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TXP_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TXP_MBAR_DONE_%=;\n"
+        "bra TXP_MBAR_WAIT_%=;\n"
+        "TXP_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const uint32_t smem_dst, const void* tmap, const uint32_t x, const uint32_t y, const uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+// exactly one lane of a converged warp (so that ptxas issues the uniform-datapath UTMALDG once, without a loop over active lanes)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+struct alignas(64) TmaDesc { unsigned char bytes[128]; };       // CUtensorMap (opaque, 64-byte aligned) without <cuda.h> in device code
+
+template <int THREADS, int STAGES>
+constexpr size_t lattice_tma_smem() { return lattice_image_smem<THREADS, STAGES>() + (size_t)(THREADS / 32) * STAGES * 8; }
+
+template <int FMT, int THREADS, int MIN_CTAS, int STAGES>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) alpha_lattice_tma_kernel(const __grid_constant__ TmaDesc tmap, const __grid_constant__ BlockSource src,
+                                                                             uint8_t* __restrict__ out, const uint32_t ntiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4* tab = reinterpret_cast<uint4*>(smem_raw);
+    uint4* ring = tab + 512;                                                          // [warp][stage][row][lane]
+    WarpQueue* queues = reinterpret_cast<WarpQueue*>(ring + THREADS * STAGES * 4);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(queues + THREADS / 32);   // [warp][stage]
+    for (int i = threadIdx.x; i < 512; i += THREADS) tab[i] = g_alpha_lattice[i];
+    if (threadIdx.x < (THREADS / 32) * STAGES) mbar_init((uint32_t)__cvta_generic_to_shared(bars + threadIdx.x), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    __syncthreads();
+    // the warp index through a shuffle: ptxas then knows that everything derived from it (ring / barrier addresses, tile
+    // coordinates) is warp-uniform and keeps it in uniform registers, which is where UTMALDG takes its operands from
+    const uint32_t warp = __shfl_sync(FULL, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    WarpQueue& q = queues[warp];
+    uint32_t qa = 0, qb[3] = {0, 0, 0};
+    const uint32_t stride = gridDim.x * (THREADS / 32);
+    const uint32_t tiles_per_row = src.bw >> 5, nblocks = (uint32_t)src.nblocks, full_rows = src.h >> 2;   // bw % 32 == 0 (host)
+    const uint4* my = ring + (warp * STAGES * 4) * 32 + lane;                         // + (stage * 4 + row) * 32
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + (warp * STAGES * 4) * 32);
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bars + warp * STAGES);
+
+    // prefetch stream (warp-uniform): tile index -> (block row, tile in row) STAGES-1 tiles ahead, advanced incrementally
+    const uint32_t tile0 = blockIdx.x * (THREADS / 32) + warp;
+    uint32_t pt = tile0, pty = pt / tiles_per_row, ptx = pt - pty * tiles_per_row, pst = 0;
+    const uint32_t step_q = stride / tiles_per_row, step_r = stride - step_q * tiles_per_row;
+    uint32_t staged = 0;                                                              // bit k: the tile issued k prefetches ago was staged
+    auto prefetch = [&]() {
+        const bool ok = pt < ntiles && pty < full_rows;                               // warp-uniform
+        if (ok) {
+            if (elect_one()) {
+                const uint32_t bar = bar_s + pst * 8;
+                mbar_expect_tx(bar, 4 * 32 * 16);
+                tma_load_2d(ring_s + pst * (4 * 32 * 16), &tmap, ptx * 128, pty * 4, bar);
+            }
+        }
+        staged = (staged << 1) | (ok ? 1u : 0u);
+        pt += stride; ptx += step_r; pty += step_q;
+        if (ptx >= tiles_per_row) { ptx -= tiles_per_row; ++pty; }
+        pst = pst + 1 == STAGES ? 0 : pst + 1;
+    };
+#pragma unroll
+    for (int i = 0; i < STAGES - 1; ++i) prefetch();
+
+    // One parity bit for all stages: it flips when the stage index wraps.  A warp's tiles are visited in increasing order and a
+    // tile that is not staged (partial bottom row, past the image) is followed only by tiles that are not staged either, so no
+    // barrier is ever waited on after a round in which it was skipped.
+    uint32_t st = 0, phase = 0;
+#pragma unroll 1
+    for (uint32_t tile = tile0; tile < ntiles; tile += stride) {
+        prefetch();                                       // into the stage every lane finished reading last iteration (__syncwarp in queue_push_drain)
+        const uint32_t b = tile * 32 + lane;
+        bool todo0 = false, todo1 = false;
+        uint32_t reload = 0, VR[4] = {0, 0, 0, 0}, VG[4] = {0, 0, 0, 0};
+        if ((staged >> (STAGES - 1)) & 1u) {              // warp-uniform
+            mbar_wait(bar_s + st * 8, phase);
+            if (b < nblocks) {
+                uint32_t px[16];
+                const uint4* sp = my + st * (4 * 32);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { const uint4 v = sp[r * 32]; px[4 * r] = v.x; px[4 * r + 1] = v.y; px[4 * r + 2] = v.z; px[4 * r + 3] = v.w; }
+                alpha_block_body<FMT>(px, tab, out, b, todo0, VR, todo1, VG);
+            }
+        } else if (b < nblocks) {                         // partial bottom row
+            todo0 = true; todo1 = FMT == BC5; reload = ITEM_RELOAD;
+        }
+        queue_push_drain<FMT>(q, qa, qb, lane, src, out, tab, b | reload, todo0, VR, todo1, VG);
+        if (++st == STAGES) { st = 0; phase ^= 1u; }
+    }
+    // copies issued for tiles past the end were never started (ok == false), so nothing is in flight here
     queue_flush<FMT>(q, qa, qb, lane, src, out, tab);
 }
 

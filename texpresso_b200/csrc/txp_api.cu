@@ -14,6 +14,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda.h>                 // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved at run time through cudaGetDriverEntryPoint; libcuda is not linked)
+
 #include "../../include/texpresso_b200.h"
 #include "single_lut_data.h"
 #include "txp_common.cuh"
@@ -228,7 +230,6 @@ constexpr int MAX_DEVICES = 64;
 constexpr int NSLOTS = TXP_NSLOTS;   // pipeline slots (stream + staging) per device
 constexpr size_t CHUNK_BYTES = 32u << 20;       // largest input chunk per pipeline stage
 constexpr size_t MIN_CHUNK_BYTES = 2u << 20;    // smallest chunk worth a separate launch + copy
-constexpr size_t LANE_CHUNK_BYTES_MAX = 64u << 20;   // largest chunk taken so that a ClusterFit launch reaches the lane-per-block threshold
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -289,6 +290,7 @@ static int ensure_ctx(int dev, DeviceCtx** out) {
         TXP_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
 #define TXP_LATTICE_ATTR(F, T, M)                                                                                                                                      \
         TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_image_smem<T, LATTICE_STAGES>())); \
+        TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_tma_kernel<F, T, M, LATTICE_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_tma_smem<T, LATTICE_STAGES>())); \
         TXP_CUDA(cudaFuncSetAttribute(alpha_lattice_kernel<F, T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_smem<T>()))
         TXP_LATTICE_ATTR(BC4, 256, 2); TXP_LATTICE_ATTR(BC4, 512, 1);
         TXP_LATTICE_ATTR(BC5, 256, 2); TXP_LATTICE_ATTR(BC5, 512, 1);
@@ -460,6 +462,33 @@ static int launch_cluster_warp(DeviceCtx& ctx, int format, const BlockSource& sr
     return TXP_OK;
 }
 
+// 2-D tensor map over a tightly packed RGBA8 image (uint32 elements, w x h), box = one strip of 32 blocks: 128 pixels x 4 rows
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+static bool make_strip_tensor_map(const BlockSource& src, TmaDesc* out) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {src.w, src.h};
+    const cuuint64_t strides[1] = {(cuuint64_t)src.w * 4};
+    const cuuint32_t box[2] = {128, 4}, estr[2] = {1, 1};
+    const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(src.rgba), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    std::memcpy(out, &m, sizeof m);
+    return true;
+}
+
 // ---- kernel launchers -------------------------------------------------------------------------------
 // concurrent: the caller keeps several launches in flight on different streams (texture batches), so a launch does not
 // have to fill the GPU on its own for the lane-per-block kernels to pay off
@@ -478,7 +507,11 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         const uint32_t ntiles = (uint32_t)((src.nblocks + 31) / 32);                                                  \
         const uint32_t need = (ntiles + (T) / 32 - 1) / ((T) / 32), cap = (uint32_t)ctx.sm_count * (M);               \
         const uint32_t grid = need < cap ? need : cap;                                                                \
-        if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged && (uint64_t)src.w * src.h * 4 < 0xF0000000ull) {                                           \
+        TmaDesc tmap;                                                                                                 \
+        if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged && alpha_tma && (src.bw % 32) == 0 && src.h >= 4 && make_strip_tensor_map(src, &tmap)) { \
+            /* strips of 32 blocks staged with one cp.async.bulk.tensor each (TMA) */                                 \
+            alpha_lattice_tma_kernel<F, T, M, LATTICE_STAGES><<<grid, T, lattice_tma_smem<T, LATTICE_STAGES>(), st>>>(tmap, src, d_out, ntiles); \
+        } else if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged && (uint64_t)src.w * src.h * 4 < 0xF0000000ull) {                                           \
             /* plain aligned image: cp.async-staged kernel; per-iteration block stride as (quotient, remainder) of bw */ \
             const uint64_t step = (uint64_t)grid * ((T) / 32) * 32;                                                   \
             alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES><<<grid, T, lattice_image_smem<T, LATTICE_STAGES>(), st>>>(             \
@@ -488,6 +521,7 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         }                                                                                                             \
     } while (0)
         static const bool alpha_staged = [] { const char* e = getenv("TXP_ALPHA_STAGED"); return !e || atoi(e) != 0; }();
+        static const bool alpha_tma = [] { const char* e = getenv("TXP_ALPHA_TMA"); return !e || atoi(e) != 0; }();
         // launch shapes measured with tools/micro/alpha_ab.cu (profiles/README.md): one 512-thread CTA per SM (16 warps,
         // 4 per scheduler, <= 128 registers) is the fastest; warp counts that are not a multiple of 4 per SM lose 10-15 %.
         if (format == BC4) {
@@ -611,11 +645,16 @@ static void slots_abandon(DeviceCtx& c) {
     cudaGetLastError();
 }
 
-// Rows per pipeline chunk for block rows [row0,row1) of a w-wide image.
+// Rows per pipeline chunk for a shard of `rows` block rows of a w-wide image.
 //  * at least ~6 chunks per call so that H2D, kernels and D2H of neighbouring chunks overlap (small shards at 8 ranks)
 //  * ClusterFit searches are compute-bound (>= 1 ms per 16 MiB against 0.3 ms of H2D) and their lane-per-block kernels want
-//    launches of at least lane_min blocks (3 x that for IterativeClusterFit, see launch_encode): a shard that holds two or
-//    more such launches is cut into chunks of that many blocks, rounded UP to whole block rows
+//    launches of at least lane_min blocks: a shard that holds two or more such launches is cut into chunks of exactly that many
+//    blocks, rounded UP to whole block rows (measured, profiles/iter_e2e_r02.txt: 16 MiB chunks 18.56 ms, 32 MiB 18.83 ms,
+//    64 MiB 19.50 ms end to end for BC3 ClusterFit 8192^2 against 18.42 ms device-resident -- the copies of the first and the
+//    last chunk are the exposed ones)
+//  * IterativeClusterFit: every launch ends in a drain tail of up to 8 orderings per block, twice for BC1, so few large launches:
+//    chunks of ~ITER_CHUNK_BYTES (same file: 48 MiB chunks 60.6 ms, 96 MiB 57.6 ms, 192 MiB 59.2 ms against 53.7 ms)
+constexpr size_t ITER_CHUNK_BYTES = 96u << 20;
 static size_t pipeline_rows_per_chunk(int format, const txp_params* p, size_t w, size_t rows) {
     const size_t bw = (w + 3) / 4, row_bytes = 16 * w;
     size_t chunk_bytes = rows * row_bytes / 6;
@@ -624,9 +663,13 @@ static size_t pipeline_rows_per_chunk(int format, const txp_params* p, size_t w,
     size_t rows_per_chunk = chunk_bytes / row_bytes;
     if (format <= BC3 && p->algorithm != RANGE_FIT) {
         const long long lm = g_lane_min_blocks.load(std::memory_order_relaxed);
-        const size_t lane_blocks = (size_t)(lm > 0 ? lm : 1) * (p->algorithm == ITERATIVE_CLUSTER_FIT ? 3 : 1);
-        const size_t lane_rows = (lane_blocks + bw - 1) / bw;                      // ceil: the launch must not fall below the threshold
-        if (lane_rows * row_bytes <= LANE_CHUNK_BYTES_MAX && rows >= 2 * lane_rows && rows_per_chunk < lane_rows) rows_per_chunk = lane_rows;
+        const size_t lane_rows = ((size_t)(lm > 0 ? lm : 1) + bw - 1) / bw;                        // ceil: the launch must not fall below the threshold
+        if (p->algorithm == ITERATIVE_CLUSTER_FIT) {
+            const size_t iter_rows = ITER_CHUNK_BYTES / row_bytes;
+            if (iter_rows >= 3 * lane_rows && rows >= 3 * lane_rows + lane_rows / 2) rows_per_chunk = iter_rows;
+        } else if (rows >= 2 * lane_rows) {
+            rows_per_chunk = lane_rows;
+        }
     }
     const int force_mib = g_chunk_mib.load(std::memory_order_relaxed);
     if (force_mib > 0) rows_per_chunk = ((size_t)force_mib << 20) / row_bytes;
@@ -636,17 +679,28 @@ static size_t pipeline_rows_per_chunk(int format, const txp_params* p, size_t w,
 // Chunk sizes (block rows) of the H2D -> kernels -> D2H pipeline for a shard of `rows` block rows.
 //  * default: uniform chunks, the first one quarter-sized (its H2D copy is the only one nothing overlaps); for ClusterFit the rows
 //    after it are spread evenly, so that no short last chunk falls below the lane-per-block threshold
+//  * IterativeClusterFit: the first chunk is half a lane launch (131 072 blocks, 8 MiB: its 2 ms of kernels cover the copy of a
+//    96 MiB chunk), the rest is spread evenly over chunks of ~ITER_CHUNK_BYTES
 //  * ClusterFit shards of fewer than three lane-sized chunks (8192^2 over 8 GPUs: 256 block rows per rank): geometric growth
-//    c, G c, rest -- every chunk's kernels cover the next chunk's copy (compute : PCIe time is ~3.6 : 1 for ClusterFit, ~10 : 1
-//    for IterativeClusterFit) and only a small copy is exposed at either end
+//    c, G c, rest -- every chunk's kernels cover the next chunk's copy (compute : PCIe time is ~3.6 : 1) and only a small copy
+//    is exposed at either end (profiles/iter_e2e_r02.txt: 2.83 ms instead of 2.86 ms for BC3, 3.12 instead of 3.25 ms for BC1)
 static std::vector<size_t> pipeline_plan(int format, const txp_params* p, size_t w, size_t rows) {
     const size_t bw = (w + 3) / 4;
     size_t rows_per_chunk = pipeline_rows_per_chunk(format, p, w, rows);
     std::vector<size_t> plan;
-    const bool cluster = format <= BC3 && p->algorithm != RANGE_FIT;
+    const bool cluster = format <= BC3 && p->algorithm != RANGE_FIT, forced = g_chunk_mib.load(std::memory_order_relaxed) != 0;
     const int growth = g_plan_growth.load(std::memory_order_relaxed);
-    if (cluster && growth > 1 && g_chunk_mib.load(std::memory_order_relaxed) == 0 && rows < 3 * rows_per_chunk && rows * bw >= 131072) {
-        const size_t G = (size_t)growth * (p->algorithm == ITERATIVE_CLUSTER_FIT ? 2 : 1);
+    if (cluster && !forced && p->algorithm == ITERATIVE_CLUSTER_FIT && rows > rows_per_chunk && rows_per_chunk * 16 * w >= ITER_CHUNK_BYTES / 2) {
+        const long long lm = g_lane_min_blocks.load(std::memory_order_relaxed);
+        size_t first = ((size_t)(lm > 0 ? lm : 1) / 2 + bw - 1) / bw;
+        if (first < 1) first = 1;
+        const size_t rest = rows - first, n = (rest + rows_per_chunk - 1) / rows_per_chunk;
+        plan.push_back(first);
+        plan.push_back((rest + n - 1) / n);
+        return plan;
+    }
+    if (cluster && !forced && growth > 1 && p->algorithm == CLUSTER_FIT && rows < 3 * rows_per_chunk && rows * bw >= 131072) {
+        const size_t G = (size_t)growth;
         const size_t min_rows = (16384 + bw - 1) / bw;                       // a launch of at least 16 Ki blocks
         size_t c1 = (rows + G * G + G) / (1 + G + G * G);
         if (c1 < min_rows) c1 = min_rows;

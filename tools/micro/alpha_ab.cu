@@ -3,6 +3,8 @@
 // every output bit for bit against the literal kernel (alpha_encode_kernel).  No Python, compiles in seconds.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -lineinfo [-DTXP_LAT_...] -o alpha_ab alpha_ab.cu
 #include <cstdio>
+#include <cstring>
+#include <cuda.h>
 #include <cstdlib>
 #include <vector>
 #include "../../texpresso_b200/csrc/txp_common.cuh"
@@ -63,16 +65,50 @@ void run_shape(const BlockSource& src, uint8_t* out, const uint8_t* ref, int sms
     cudaFree(bad);
 }
 
+// the TMA-staged kernel (one cp.async.bulk.tensor per 32-block strip) in the same launch shape
+static bool make_map(const BlockSource& src, TmaDesc* out) {
+    void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || !fp) return false;
+    typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    CUtensorMap m; const cuuint64_t dims[2] = {src.w, src.h}, strides[1] = {(cuuint64_t)src.w * 4}; const cuuint32_t box[2] = {128, 4}, es[2] = {1, 1};
+    if (((Fn)fp)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)src.rgba, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    memcpy(out, &m, sizeof m); return true;
+}
+template <int FMT, int T, int M, int S>
+void run_shape_tma(const BlockSource& src, uint8_t* out, const uint8_t* ref, int sms, const char* tag) {
+    cudaFuncSetAttribute(alpha_lattice_tma_kernel<FMT, T, M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lattice_tma_smem<T, S>());
+    TmaDesc tm; if (!make_map(src, &tm)) { printf("tensor map failed\n"); return; }
+    const uint32_t ntiles = (uint32_t)((src.nblocks + 31) / 32), grid = (uint32_t)sms * M;
+    const size_t bs = FMT == BC4 ? 8 : 16;
+    cudaMemset(out, 0xEE, src.nblocks * bs);
+    auto f = [&] { alpha_lattice_tma_kernel<FMT, T, M, S><<<grid, T, lattice_tma_smem<T, S>()>>>(tm, src, out, ntiles); };
+    const float ms = timeit(f, 5);
+    unsigned long long* bad; cudaMallocManaged(&bad, 8); *bad = 0;
+    const size_t n2 = src.nblocks * bs / 8;
+    cmp<<<(unsigned)((n2 + 255) / 256), 256>>>((const uint2*)out, (const uint2*)ref, n2, bad);
+    cudaDeviceSynchronize();
+    const double bytes = (double)src.nblocks * (64 + bs);
+    printf("%-6s %s TMA T=%3d M=%d S=%d  %7.4f ms  %5.1f%% of 6455.6 GB/s  mismatches=%llu  %s\n", tag, FMT == BC4 ? "BC4" : "BC5", T, M, S, ms,
+           100.0 * bytes / (ms * 1e-3) / 6455.6e9, *bad, cudaGetErrorString(cudaGetLastError()));
+    cudaFree(bad);
+}
+
 template <int FMT> void run_fmt(const BlockSource& src, int sms, const char* tag) {
     const size_t bs = FMT == BC4 ? 8 : 16;
     uint8_t *out, *ref; cudaMalloc(&out, src.nblocks * bs); cudaMalloc(&ref, src.nblocks * bs);
     alpha_encode_kernel<FMT, 128, 6><<<(unsigned)((src.nblocks + 127) / 128), 128>>>(src, ref);
     cudaDeviceSynchronize();
-    run_shape<FMT, 256, 2, 3>(src, out, ref, sms, tag);
-#ifndef AB_ONE_SHAPE
     run_shape<FMT, 512, 1, 3>(src, out, ref, sms, tag);
-    run_shape<FMT, 512, 1, 2>(src, out, ref, sms, tag);
-    run_shape<FMT, 640, 1, 2>(src, out, ref, sms, tag);
+    run_shape_tma<FMT, 512, 1, 3>(src, out, ref, sms, tag);
+    run_shape<FMT, 512, 1, 3>(src, out, ref, sms, tag);
+    run_shape_tma<FMT, 512, 1, 3>(src, out, ref, sms, tag);
+#ifndef AB_ONE_SHAPE
+    run_shape_tma<FMT, 512, 1, 2>(src, out, ref, sms, tag);
+    run_shape_tma<FMT, 512, 1, 4>(src, out, ref, sms, tag);
+    run_shape_tma<FMT, 256, 2, 3>(src, out, ref, sms, tag);
+    run_shape_tma<FMT, 640, 1, 2>(src, out, ref, sms, tag);
 #endif
     cudaFree(out); cudaFree(ref);
 }
