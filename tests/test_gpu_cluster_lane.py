@@ -88,8 +88,8 @@ def test_lane_equals_warp_kernel_and_auto_threshold():
             bs = 8 if fmt == 0 else 16
             cp = T.Params(T.Algorithm(alg))._c()
             outs, launches = {}, {}
-            _lib.check(L.txp_debug_set(2, 100))               # hybrid: every partly filled last round goes to the warp kernel
             for name, v in (("auto", 0), ("fused", 1), ("warp", 2), ("lane", 3), ("hybrid", 4)):
+                _lib.check(L.txp_debug_set(2, 100 if name == "hybrid" else 0))   # hybrid: every partly filled last round goes to the warp kernel
                 _lib.check(L.txp_debug_set(0, v))
                 out = torch.zeros((w // 4) * (h // 4) * bs, dtype=torch.uint8, device="cuda")
                 n0 = T.kernel_launches()

@@ -49,7 +49,13 @@ __device__ uint4 g_alpha_lattice[512];            // TXP_ALPHA_LATTICE (alpha_la
 #define TXP_LAT_MM 0       // min / max: 0 = VIMNMX3 trees, 1 = two-input VIMNMX
 #endif
 
+#ifndef TXP_LAT_LIFT
+#define TXP_LAT_LIFT 1     // regular path, pixel -> fp32: 1 = IDP.4A (FMA pipe): 1.5*2^16 + v with the byte at mantissa bits 7..14; 0 = PRMT (ALU pipe): 1.5*2^15 + v, bits 8..15
+#endif
 constexpr uint32_t MAGIC15 = 0x47400000u;         // 1.5 * 2^15 as fp32 bits
+constexpr uint32_t MAGIC16 = 0x47C00000u;         // 1.5 * 2^16 as fp32 bits
+constexpr int LIFT_SHIFT = TXP_LAT_LIFT ? 7 : 8;  // position of the pixel value inside the lifted word
+constexpr uint32_t LIFT_MAGIC = TXP_LAT_LIFT ? MAGIC16 : MAGIC15;
 constexpr float MAGIC23 = 12582912.0f;            // 1.5 * 2^23
 
 // PRMT with the hardware selector semantics (bit 3 of a nibble = sign replication).  __byte_perm() promises to ignore
@@ -147,11 +153,11 @@ __device__ __forceinline__ bool alpha_fit_lattice(const uint32_t vm[16], const u
     for (int i = 3; i < 15; i += 2) { mn = __vimin3_u32(mn, vm[i], vm[i + 1]); mx = __vimax3_u32(mx, vm[i], vm[i + 1]); }
     mn = min(mn, vm[15]); mx = max(mx, vm[15]);
 #endif
-    const uint32_t span = mx - mn;                                     // r << 8
-    if (!(mn > MAGIC15 && mx < (MAGIC15 | 0xFF00u) && span >= (7u << 8))) return false;
+    const uint32_t span = mx - mn;                                     // r << LIFT_SHIFT
+    if (!(mn > LIFT_MAGIC && mx < (LIFT_MAGIC | (255u << LIFT_SHIFT)) && span >= (7u << LIFT_SHIFT))) return false;
 
-    const uint4 e5 = tab[span >> 7], e7 = tab[(span >> 7) + 1];        // row r = two uint4
-    const uint32_t lo = (mn >> 8) & 255u, hi = (mx >> 8) & 255u;
+    const uint4 e5 = tab[span >> (LIFT_SHIFT - 1)], e7 = tab[(span >> (LIFT_SHIFT - 1)) + 1];        // row r = two uint4
+    const uint32_t lo = (mn >> LIFT_SHIFT) & 255u, hi = (mx >> LIFT_SHIFT) & 255u;
     uint32_t s5[4], s7[4];
     // 5-point book from lo: x = v - lo, origin = lo - beta5, codes lo + offs
     const int err5 = lattice_book(vm, V, __fsub_rn(__uint_as_float(mn), __uint_as_float(e5.y)), __uint_as_float(e5.x),
@@ -188,7 +194,9 @@ __device__ __forceinline__ void alpha_fit_block(const uint32_t px[16], const uin
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-#if TXP_LAT_VMR == 0
+#if TXP_LAT_LIFT
+        vm[i] = __dp4a(px[i], 0x00000080u, MAGIC16);                                 // 1.5 * 2^16 + R, as an integer add on the FMA pipe
+#elif TXP_LAT_VMR == 0
         vm[i] = prmt(MAGIC15, px[i], 0x3240u);                                       // bytes (0x00, R, 0x40, 0x47)
 #elif TXP_LAT_VMR == 1
         vm[i] = ((px[i] << 8) & 0xFF00u) | MAGIC15;
@@ -201,7 +209,9 @@ __device__ __forceinline__ void alpha_fit_block(const uint32_t px[16], const uin
     if (FMT == BC5) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-#if TXP_LAT_VMG == 0
+#if TXP_LAT_LIFT
+            vm[i] = __dp4a(px[i], 0x00008000u, MAGIC16);
+#elif TXP_LAT_VMG == 0
             vm[i] = prmt(MAGIC15, px[i], 0x3250u);
 #elif TXP_LAT_VMG == 1
             vm[i] = (px[i] & 0xFF00u) | MAGIC15;

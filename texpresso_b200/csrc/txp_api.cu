@@ -386,32 +386,29 @@ static uint64_t lane_wave_blocks(const DeviceCtx& ctx) { return (uint64_t)ctx.sm
 // K1 (thread per block; also emits the points of every colour set and a window-sorted permutation) -> K2L (lane per block)
 static int launch_cluster_lane(DeviceCtx& ctx, int format, const BlockSource& src, const EncodeParams& e, uint8_t* d_out, cudaStream_t st,
                                const uint64_t first_block, const uint64_t nblocks) {
-    // at most LANE_CHUNK_BLOCKS blocks per launch pair (292 B of scratch per block), split evenly so that no launch is small
+    // at most LANE_CHUNK_BLOCKS blocks per launch pair (100-104 B of scratch per block), split evenly so that no launch is small
     const uint64_t n_chunks = (nblocks + LANE_CHUNK_BLOCKS - 1) / LANE_CHUNK_BLOCKS;
     const uint64_t chunk_blocks = ((nblocks + n_chunks - 1) / n_chunks + SETUP_WINDOW - 1) / SETUP_WINDOW * SETUP_WINDOW;
     for (uint64_t off = 0; off < nblocks; off += chunk_blocks) {
         const uint64_t first = first_block + off;
         const uint32_t n = (uint32_t)std::min<uint64_t>(chunk_blocks, nblocks - off);
         const size_t n32 = ((size_t)n + 31) & ~size_t(31);
-        const size_t pt_bytes = n32 * 16 * sizeof(float4), setup_bytes = n32 * sizeof(uint4), remap_bytes = n32 * sizeof(uint2);
-        const size_t word_bytes = n32 * sizeof(uint32_t);
+        const size_t rec_bytes = n32 * (size_t)rec_quads(true, e.alpha_weighted != 0) * sizeof(uint4), word_bytes = n32 * sizeof(uint32_t);
         uint8_t* scratch = nullptr;
-        TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), pt_bytes + setup_bytes + remap_bytes + 2 * word_bytes + 256, ctx.pool, st));
-        float4* pt = reinterpret_cast<float4*>(scratch);
-        uint4* setup = reinterpret_cast<uint4*>(scratch + pt_bytes);
-        uint2* remap = reinterpret_cast<uint2*>(scratch + pt_bytes + setup_bytes);
-        uint32_t* perm = reinterpret_cast<uint32_t*>(scratch + pt_bytes + setup_bytes + remap_bytes);
+        TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), rec_bytes + 2 * word_bytes + 256, ctx.pool, st));
+        uint4* rec = reinterpret_cast<uint4*>(scratch);
+        uint32_t* perm = reinterpret_cast<uint32_t*>(scratch + rec_bytes);
         uint32_t* carry = perm + n32;
         uint32_t* counters = carry + n32;
         const unsigned g1 = (unsigned)((n + SETUP_WINDOW - 1) / SETUP_WINDOW), g2 = (unsigned)((n + LANE_THREADS - 1) / LANE_THREADS);
-        if (format == BC1) cluster_setup_sorted_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
-        else if (format == BC2) cluster_setup_sorted_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
-        else cluster_setup_sorted_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, remap, pt, perm, first, n);
+        if (format == BC1) cluster_setup_sorted_kernel<BC1><<<g1, ROLL_THREADS, 0, st>>>(src, e, d_out, rec, perm, first, n);
+        else if (format == BC2) cluster_setup_sorted_kernel<BC2><<<g1, ROLL_THREADS, 0, st>>>(src, e, d_out, rec, perm, first, n);
+        else cluster_setup_sorted_kernel<BC3><<<g1, ROLL_THREADS, 0, st>>>(src, e, d_out, rec, perm, first, n);
         cudaError_t aux_err = cudaSuccess;
         if (e.algorithm == CLUSTER_FIT) {
-            if (format == BC1) cluster_lane_kernel<BC1><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
-            else if (format == BC2) cluster_lane_kernel<BC2><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
-            else cluster_lane_kernel<BC3><<<g2, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, d_out, first, n);
+            if (format == BC1) cluster_lane_kernel<BC1><<<g2, LANE_THREADS, 0, st>>>(e, rec, perm, d_out, first, n);
+            else if (format == BC2) cluster_lane_kernel<BC2><<<g2, LANE_THREADS, 0, st>>>(e, rec, perm, d_out, first, n);
+            else cluster_lane_kernel<BC3><<<g2, LANE_THREADS, 0, st>>>(e, rec, perm, d_out, first, n);
             g_launches.fetch_add(2, std::memory_order_relaxed);
             g_path_lane.fetch_add(1, std::memory_order_relaxed);
         } else {
@@ -420,13 +417,13 @@ static int launch_cluster_lane(DeviceCtx& ctx, int format, const BlockSource& sr
             aux_err = cudaMemsetAsync(counters, 0, 256, st);
             const unsigned cap = (unsigned)ctx.sm_count * TXP_LANE_ITER_MIN_CTAS, g3 = g2 < cap ? g2 : cap;
             if (format == BC1) {
-                cluster_lane_iter_kernel<BC1, true><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
-                cluster_lane_iter_kernel<BC1, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters + 1, first, n);
+                cluster_lane_iter_kernel<BC1, true><<<g3, LANE_THREADS, 0, st>>>(e, rec, perm, carry, d_out, counters, first, n);
+                cluster_lane_iter_kernel<BC1, false><<<g3, LANE_THREADS, 0, st>>>(e, rec, perm, carry, d_out, counters + 1, first, n);
                 g_launches.fetch_add(1, std::memory_order_relaxed);
             } else if (format == BC2) {
-                cluster_lane_iter_kernel<BC2, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+                cluster_lane_iter_kernel<BC2, false><<<g3, LANE_THREADS, 0, st>>>(e, rec, perm, carry, d_out, counters, first, n);
             } else {
-                cluster_lane_iter_kernel<BC3, false><<<g3, LANE_THREADS, 0, st>>>(e, setup, remap, pt, perm, carry, d_out, counters, first, n);
+                cluster_lane_iter_kernel<BC3, false><<<g3, LANE_THREADS, 0, st>>>(e, rec, perm, carry, d_out, counters, first, n);
             }
             g_launches.fetch_add(2, std::memory_order_relaxed);
         }
@@ -447,9 +444,9 @@ static int launch_cluster_warp(DeviceCtx& ctx, int format, const BlockSource& sr
     uint4* setup = nullptr;
     TXP_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&setup), (size_t)nblocks * sizeof(uint4), ctx.pool, st));
     const unsigned g1 = (unsigned)((nblocks + 127) / 128);
-    if (format == BC1) cluster_setup_kernel<BC1><<<g1, 128, 0, st>>>(src, e, d_out, setup, first, n);
-    else if (format == BC2) cluster_setup_kernel<BC2><<<g1, 128, 0, st>>>(src, e, d_out, setup, first, n);
-    else cluster_setup_kernel<BC3><<<g1, 128, 0, st>>>(src, e, d_out, setup, first, n);
+    if (format == BC1) cluster_setup_kernel<BC1><<<g1, ROLL_THREADS, 0, st>>>(src, e, d_out, setup, first, n);
+    else if (format == BC2) cluster_setup_kernel<BC2><<<g1, ROLL_THREADS, 0, st>>>(src, e, d_out, setup, first, n);
+    else cluster_setup_kernel<BC3><<<g1, ROLL_THREADS, 0, st>>>(src, e, d_out, setup, first, n);
     if (format == BC1) colour_search_kernel<BC1><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out, first, n);
     else if (format == BC2) colour_search_kernel<BC2><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out, first, n);
     else colour_search_kernel<BC3><<<grid, threads, COLOUR_SMEM, st>>>(src, e, setup, d_out, first, n);
@@ -545,10 +542,10 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
 #undef TXP_ALPHA_LAUNCH
     } else if (e.algorithm == RANGE_FIT) {
         // RangeFit: one thread per block (txp_range.cuh)
-        const unsigned grid = (unsigned)((src.nblocks + 127) / 128);
-        if (format == BC1) range_encode_kernel<BC1><<<grid, 128, 0, st>>>(src, e, d_out);
-        else if (format == BC2) range_encode_kernel<BC2><<<grid, 128, 0, st>>>(src, e, d_out);
-        else range_encode_kernel<BC3><<<grid, 128, 0, st>>>(src, e, d_out);
+        const unsigned grid = (unsigned)((src.nblocks + ROLL_THREADS - 1) / ROLL_THREADS);
+        if (format == BC1) range_encode_kernel<BC1><<<grid, ROLL_THREADS, 0, st>>>(src, e, d_out);
+        else if (format == BC2) range_encode_kernel<BC2><<<grid, ROLL_THREADS, 0, st>>>(src, e, d_out);
+        else range_encode_kernel<BC3><<<grid, ROLL_THREADS, 0, st>>>(src, e, d_out);
     } else {
         const int variant = g_colour_variant.load(std::memory_order_relaxed);
         if (variant == 1) {                                                                        // single-kernel variant kept for A/B measurements

@@ -148,14 +148,34 @@ __device__ __forceinline__ float4 lane_range_sum(const float4* col, const int a,
     return acc;
 }
 
+// ---- the block's points, from its record (layout: txp_cluster_setup.cuh) -----------------------------------------------------------
+// tabs: [0..255] c / 255 (colourset.rs:65-67), [256 + n] sqrt(n) for n = 0..16 (colourset.rs:107-109 with pixel-count weights)
+constexpr int LANE_TABS = 256 + 17;
+__device__ __forceinline__ void lane_tabs_init(float* tabs, const int tid) {
+    for (int i = tid; i < LANE_TABS; i += LANE_THREADS) tabs[i] = i < 256 ? fdiv((float)i, 255.0f) : __fsqrt_rn((float)(i - 256));
+}
+
+// point q of the set as (x, y, z, weight)
+__device__ __forceinline__ float4 lane_point(const uint4* __restrict__ rec, const bool alpha_weighted, const float* __restrict__ tabs, const uint32_t q) {
+    const uint32_t k = __ldg(reinterpret_cast<const uint32_t*>(rec + 1) + q);
+    const float w = alpha_weighted ? __ldg(reinterpret_cast<const float*>(rec + 5) + q) : tabs[256 + (k >> 24)];
+    return make_float4(tabs[k & 255u], tabs[(k >> 8) & 255u], tabs[(k >> 16) & 255u], w);
+}
+
 // points_weights for the ordering `ow` (cluster.rs:123-133): colw[m] = (x, y, z, 1) * w of point ow[m]; zero guard at [count].
-// pt = the block's points in set order (global memory, written by the setup kernel).
-__device__ __forceinline__ void lane_build_pw(const float4* __restrict__ pt, const unsigned long long ow, const int count, float4* colw) {
+__device__ __forceinline__ void lane_build_pw(const uint4* __restrict__ rec, const bool alpha_weighted, const float* __restrict__ tabs,
+                                              const unsigned long long ow, const int count, float4* colw) {
     for (int m = 0; m < count; ++m) {
-        const float4 q = __ldg(pt + ((ow >> (4 * m)) & 15ull));
+        const float4 q = lane_point(rec, alpha_weighted, tabs, (uint32_t)(ow >> (4 * m)) & 15u);
         colw[m * LANE_THREADS] = make_float4(mul(q.x, q.w), mul(q.y, q.w), mul(q.z, q.w), q.w);
     }
     colw[count * LANE_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// pixel -> point map (colourset.rs:130-141), 4 bits per pixel
+__device__ __forceinline__ uint2 lane_remap(const uint4* __restrict__ rec, const bool alpha_weighted) {
+    const uint4 rm = __ldg(rec + (alpha_weighted ? 9 : 5));
+    return make_uint2(rm.x, rm.y);
 }
 
 struct LaneWinner { bool three; int bi, bj, bk; };
@@ -200,24 +220,27 @@ __device__ __forceinline__ uint2 lane_finish_block(const unsigned long long ow, 
 
 template <int FMT>
 __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_MIN_CTAS) cluster_lane_kernel(const EncodeParams prm,
-                                                                                       const uint4* __restrict__ setup,
-                                                                                       const uint2* __restrict__ remap,
-                                                                                       const float4* __restrict__ ptbuf,
+                                                                                       const uint4* __restrict__ rec,
                                                                                        const uint32_t* __restrict__ perm,
                                                                                        uint8_t* __restrict__ out,
                                                                                        const uint64_t first, const uint32_t n) {
     __shared__ float4 s_pw[17][LANE_THREADS];
+    __shared__ float tabs[LANE_TABS];
     const int tid = threadIdx.x;
+    lane_tabs_init(tabs, tid);
+    __syncthreads();
     float4* col = &s_pw[0][tid];
     // perm is window-sorted by cluster_setup_sorted_kernel: 32 consecutive entries are blocks of (mostly) the same shape
     const uint32_t slot = blockIdx.x * LANE_THREADS + tid;
     if (slot >= n) return;
     const uint32_t lb = __ldg(perm + slot);               // chunk-local block number
-    const uint4 su = __ldg(setup + lb);
+    const bool aw = prm.alpha_weighted != 0;
+    const uint4* r = rec + (size_t)lb * rec_quads(true, aw);
+    const uint4 su = __ldg(r);
     if (!(su.z & SETUP_SEARCH)) return;                   // finished by the setup kernel (0 or 1 points)
     const int count = (int)(su.z & 31u);
     const unsigned long long ow = (unsigned long long)su.x | ((unsigned long long)su.y << 32);
-    lane_build_pw(ptbuf + pt_index(lb, 0), ow, count, col);
+    lane_build_pw(r, aw, tabs, ow, count, col);
     const float4 xsum = lane_range_sum(col, 0, count);    // xsum_wsum (cluster.rs:125-133)
 
     LaneBest best;
@@ -235,7 +258,7 @@ __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_MIN_CTAS) cluster_lane_
         const LaneWinner w = lane_decode_key(best.key);
         Solution sol;
         lane_winner_endpoints(col, xsum, w, prm, sol);
-        block = lane_finish_block(ow, count, w, lane_565(sol.ka), lane_565(sol.kb), __ldg(remap + lb), su.z >> 16);
+        block = lane_finish_block(ow, count, w, lane_565(sol.ka), lane_565(sol.kb), lane_remap(r, aw), su.z >> 16);
     }
     uint2* out2 = reinterpret_cast<uint2*>(out);
     const uint64_t b = first + lb;
@@ -255,14 +278,14 @@ __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_MIN_CTAS) cluster_lane_
 #endif
 
 // construct_ordering (cluster.rs:78-105) for one thread: stable sort of (i, p_i . axis) for i < count, padding (0, f32::MAX)
-__device__ __forceinline__ unsigned long long lane_ordering(const float4* __restrict__ pt, const int count, const float ax, const float ay, const float az) {
+__device__ __forceinline__ unsigned long long lane_ordering(const uint4* __restrict__ rec, const float* __restrict__ tabs, const int count, const float ax, const float ay, const float az) {
     int sk[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
         int k = 0x7F7FFFFF;                               // f32::MAX, finite
         if (e < count) {
-            const float4 q = __ldg(pt + e);
-            const uint32_t bits = __float_as_uint(add(add(mul(q.x, ax), mul(q.y, ay)), mul(q.z, az)));
+            const uint32_t kq = __ldg(reinterpret_cast<const uint32_t*>(rec + 1) + e);
+            const uint32_t bits = __float_as_uint(add(add(mul(tabs[kq & 255u], ax), mul(tabs[(kq >> 8) & 255u], ay)), mul(tabs[(kq >> 16) & 255u], az)));
             // fcmp (cluster.rs:90-97): non-finite values compare Equal to each other and Greater than finite
             if ((bits & 0x7F800000u) == 0x7F800000u) k = 0x7FFFFFFF;
             else k = (bits & 0x80000000u) ? -(int)(bits & 0x7FFFFFFFu) : (int)bits;
@@ -292,9 +315,7 @@ __device__ __forceinline__ unsigned long long lane_ordering(const float4* __rest
 
 template <int FMT, bool THREE>
 __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_ITER_MIN_CTAS) cluster_lane_iter_kernel(const EncodeParams prm,
-                                                                                                 const uint4* __restrict__ setup,
-                                                                                                 const uint2* __restrict__ remap,
-                                                                                                 const float4* __restrict__ ptbuf,
+                                                                                                 const uint4* __restrict__ rec,
                                                                                                  const uint32_t* __restrict__ perm,
                                                                                                  uint32_t* __restrict__ carry,
                                                                                                  uint8_t* __restrict__ out,
@@ -302,7 +323,13 @@ __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_ITER_MIN_CTAS) cluster_
                                                                                                  const uint64_t first, const uint32_t n) {
     __shared__ float4 s_pw[17][LANE_THREADS];
     __shared__ unsigned long long s_seen[8][LANE_THREADS];
+    __shared__ float tabs[LANE_TABS];
     const int tid = threadIdx.x, lane = tid & 31;
+    lane_tabs_init(tabs, tid);
+    __syncthreads();
+    const bool aw = prm.alpha_weighted != 0;
+    const int rq = rec_quads(true, aw);
+    const uint4* r = rec;                                 // record of the block in progress
     float4* col = &s_pw[0][tid];
     uint2* out2 = reinterpret_cast<uint2*>(out);
 
@@ -334,7 +361,7 @@ __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_ITER_MIN_CTAS) cluster_
             const uint32_t avail = pool_end - pool, idx = (uint32_t)__popc(need & ((1u << lane) - 1u));
             if (!have && idx < avail) {
                 lb = __ldg(perm + pool + idx);
-                const uint4 su = __ldg(setup + lb);
+                const uint4 su = __ldg(rec + (size_t)lb * rq);
                 bool ok = (su.z & SETUP_SEARCH) != 0;
                 if (FMT == BC1 && !THREE && (su.z & SETUP_TRANSPARENT)) ok = false;      // colourfit.rs:51
                 if (ok) {
@@ -346,7 +373,8 @@ __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_ITER_MIN_CTAS) cluster_
                     it = 0; best_it = 0; best_key = LANE_NONE;
                     bsx = bsy = bsz = bex = bey = bez = 0.f;                            // best_start = best_end = zero (:165-166 / :290-291)
                     s_seen[0][tid] = ow;
-                    lane_build_pw(ptbuf + pt_index(lb, 0), ow, count, col);
+                    r = rec + (size_t)lb * rq;
+                    lane_build_pw(r, aw, tabs, ow, count, col);
                     xsum = lane_range_sum(col, 0, count);
                     have = true;
                 }
@@ -380,11 +408,11 @@ __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_ITER_MIN_CTAS) cluster_
                 if (it == 8) {
                     finished = true;
                 } else {
-                    ow = lane_ordering(ptbuf + pt_index(lb, 0), count, sub(bex, bsx), sub(bey, bsy), sub(bez, bsz));    // :248 / :388
+                    ow = lane_ordering(r, tabs, count, sub(bex, bsx), sub(bey, bsy), sub(bez, bsz));    // :248 / :388
                     for (int p = 0; p < it; ++p) finished |= (s_seen[p][tid] == ow);    // :108-120
                     if (!finished) {
                         s_seen[it][tid] = ow;
-                        lane_build_pw(ptbuf + pt_index(lb, 0), ow, count, col);
+                        lane_build_pw(r, aw, tabs, ow, count, col);
                         xsum = lane_range_sum(col, 0, count);
                     }
                 }
@@ -395,7 +423,7 @@ __global__ void __launch_bounds__(LANE_THREADS, TXP_LANE_ITER_MIN_CTAS) cluster_
                 uint2 block = make_uint2(0u, 0u);          // best_compressed starts zeroed (cluster.rs:71)
                 const bool improved = run_best < start_best;                             // :252 / :392
                 if (improved)
-                    block = lane_finish_block(best_ow, count, lane_decode_key(best_key), a565, b565, __ldg(remap + lb), zflags >> 16);
+                    block = lane_finish_block(best_ow, count, lane_decode_key(best_key), a565, b565, lane_remap(r, aw), zflags >> 16);
                 if (improved || THREE || FMT != BC1) *dst = block;                       // compress4 of BC1 keeps compress3's block otherwise
                 if (FMT == BC1 && THREE) carry[lb] = __float_as_uint(run_best);
                 have = false;

@@ -16,6 +16,7 @@
 #include <cfloat>
 #include "txp_common.cuh"
 #include "txp_alpha.cuh"
+#include "txp_block_rolled.cuh"
 
 namespace txp {
 
@@ -181,54 +182,53 @@ __device__ __forceinline__ uint32_t thread_single_rgb(const uint32_t px[16], con
     return rgb;
 }
 
-// Colour half of one block with Algorithm::RangeFit.  px: 16 RGBA words, mask: valid bits, lut: c/255 table.
+// Colour half of one block with Algorithm::RangeFit (range.rs:44-192).  px: 16 RGBA words (rewritten to keys), mask: valid
+// bits, lut: c/255 table, col: the thread's shared-memory column (txp_block_rolled.cuh).
 template <bool IS_BC1>
-__device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint32_t mask, const EncodeParams& prm,
-                                                     const float* __restrict__ lut) {
-    uint32_t gw[16];
-    const ThreadSet ts = thread_colourset<IS_BC1>(px, mask, prm.alpha_weighted != 0, gw);
+__device__ __forceinline__ uint2 range_colour_rolled(uint32_t px[16], const uint32_t mask, const EncodeParams& prm,
+                                                     const float* __restrict__ lut, float4* col) {
+    const RolledSet ts = rolled_colourset<IS_BC1>(px, mask, prm.alpha_weighted != 0, col);
     const uint32_t active16 = ts.active16, new16 = ts.new16;
-    const bool transparent = ts.transparent;
     if (active16 == 0)                                   // lib.rs:223, SURVEY Q14
         return IS_BC1 ? make_uint2(0u, 0xFFFFFFFFu) : make_uint2(0u, 0u);
     if ((new16 & (new16 - 1u)) == 0u)                    // exactly one distinct colour: lib.rs:217-222
-        return single_fit_thread<IS_BC1>(thread_single_rgb(px, active16), active16, transparent);
-    float w[16];
-    thread_weights(gw, new16, prm.alpha_weighted != 0, w);
-    const float3 axis = thread_principal_axis(px, w, lut);
-    const float vx = axis.x, vy = axis.y, vz = axis.z;
+        return single_fit_thread<IS_BC1>(rolled_single_rgb(px, active16), active16, ts.transparent);
+    rolled_fill_points<false>(px, ts, prm.alpha_weighted != 0, lut, col);
+    const float3 axis = rolled_principal_axis(col);
     // ---- range.rs:67-86: first point starts both ends; strict < / else-if > over the following points ----------
-    uint32_t ps = 0, pe = 0;
+    int is = 0, ie = 0;
     float mn = 0.f, mx = 0.f;
     bool found = false;
-#pragma unroll
+#pragma unroll 4
     for (int i = 0; i < 16; ++i) {
-        const bool is_new = (new16 >> i) & 1u;
-        const float x = lut[px[i] & 255u], y = lut[(px[i] >> 8) & 255u], z = lut[(px[i] >> 16) & 255u];
-        const float d = add(add(mul(x, vx), mul(y, vy)), mul(z, vz));
+        const float4 p = col[i * ROLL_THREADS];
+        const bool is_new = p.w > 0.0f;                  // weights of points are sqrt of positive totals
+        const float d = add(add(mul(p.x, axis.x), mul(p.y, axis.y)), mul(p.z, axis.z));
         const bool first = is_new && !found;
         const bool lower = is_new && found && d < mn;
         const bool upper = is_new && found && !(d < mn) && d > mx;
-        if (first || lower) { ps = px[i]; mn = d; }
-        if (first || upper) { pe = px[i]; mx = d; }
+        if (first || lower) { is = i; mn = d; }
+        if (first || upper) { ie = i; mx = d; }
         found = found || is_new;
     }
     // clamp to [0,1] is the identity on c/255; snap to the 5:6:5 grid (range.rs:88-98)
+    const float4 ps = col[is * ROLL_THREADS], pe = col[ie * ROLL_THREADS];
+    const float sa[3] = {ps.x, ps.y, ps.z}, ea[3] = {pe.x, pe.y, pe.z};
     const float grid[3] = {31.0f, 63.0f, 31.0f};
     const float gridrcp[3] = {1.0f / 31.0f, 1.0f / 63.0f, 1.0f / 31.0f};
     float sv[3], ev[3];
     uint32_t ks[3], ke[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float a = grid_index(grid[c], lut[(ps >> (8 * c)) & 255u]);
-        const float b = grid_index(grid[c], lut[(pe >> (8 * c)) & 255u]);
+        const float a = grid_index(grid[c], sa[c]);
+        const float b = grid_index(grid[c], ea[c]);
         ks[c] = (uint32_t)a; ke[c] = (uint32_t)b;
         sv[c] = mul(a, gridrcp[c]); ev[c] = mul(b, gridrcp[c]);
     }
     const uint32_t a565 = (ks[0] << 11) | (ks[1] << 5) | ks[2];
     const uint32_t b565 = (ke[0] << 11) | (ke[1] << 5) | ke[2];
-    const float mw[3] = {prm.wx, prm.wy, prm.wz};
-    const uint32_t inact = spread16(~active16 & 0xFFFFu) * 3u;                   // colourset.rs:134-137
+    const float wx = prm.wx, wy = prm.wy, wz = prm.wz;
+    const uint32_t act2 = spread16(active16) * 3u, inact = spread16(~active16 & 0xFFFFu) * 3u;   // colourset.rs:134-137
 
     // ---- compress3 / compress4 (range.rs:103-192, colourfit.rs:48-59) -------------------------------------------
     float best_error = FLT_MAX;
@@ -237,40 +237,44 @@ __device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint
     for (int pass = 0; pass < 2; ++pass) {
         const bool three = pass == 0;
         if (three && !IS_BC1) continue;
-        if (!three && IS_BC1 && transparent) continue;
-        float codes[4][3];
+        if (!three && IS_BC1 && ts.transparent) continue;
+        float c2[3], c3[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            codes[0][c] = sv[c]; codes[1][c] = ev[c];
             if (three) {
-                codes[2][c] = add(mul(sv[c], 0.5f), mul(ev[c], 0.5f));
-                codes[3][c] = 0.f;
+                c2[c] = add(mul(sv[c], 0.5f), mul(ev[c], 0.5f));
+                c3[c] = 0.f;
             } else {
-                codes[2][c] = add(mul(sv[c], 2.0f / 3.0f), mul(ev[c], 1.0f / 3.0f));
-                codes[3][c] = add(mul(sv[c], 1.0f / 3.0f), mul(ev[c], 2.0f / 3.0f));
+                c2[c] = add(mul(sv[c], 2.0f / 3.0f), mul(ev[c], 1.0f / 3.0f));
+                c3[c] = add(mul(sv[c], 1.0f / 3.0f), mul(ev[c], 2.0f / 3.0f));
             }
         }
         float error = 0.0f;
         uint32_t idx2 = 0;
-#pragma unroll
+#pragma unroll 2
         for (int i = 0; i < 16; ++i) {
-            const float p[3] = {lut[px[i] & 255u], lut[(px[i] >> 8) & 255u], lut[(px[i] >> 16) & 255u]};
-            float dist = FLT_MAX; uint32_t idx = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (three && j == 3) continue;
-                const float dx = mul(mw[0], sub(p[0], codes[j][0]));
-                const float dy = mul(mw[1], sub(p[1], codes[j][1]));
-                const float dz = mul(mw[2], sub(p[2], codes[j][2]));
-                const float d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
-                if (d < dist) { dist = d; idx = (uint32_t)j; }                     // range.rs:118 (strict: first wins)
+            const float4 p = col[i * ROLL_THREADS];
+            // weights are applied before squaring (range.rs:117); the first minimum wins (range.rs:118, strict <)
+            float dx = mul(wx, sub(p.x, sv[0])), dy = mul(wy, sub(p.y, sv[1])), dz = mul(wz, sub(p.z, sv[2]));
+            float dist = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+            uint32_t idx = 0;
+            dx = mul(wx, sub(p.x, ev[0])); dy = mul(wy, sub(p.y, ev[1])); dz = mul(wz, sub(p.z, ev[2]));
+            float d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+            if (d < dist) { dist = d; idx = 1u; }
+            dx = mul(wx, sub(p.x, c2[0])); dy = mul(wy, sub(p.y, c2[1])); dz = mul(wz, sub(p.z, c2[2]));
+            d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+            if (d < dist) { dist = d; idx = 2u; }
+            if (!three) {
+                dx = mul(wx, sub(p.x, c3[0])); dy = mul(wy, sub(p.y, c3[1])); dz = mul(wz, sub(p.z, c3[2]));
+                d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+                if (d < dist) { dist = d; idx = 3u; }
             }
-            error = add(error, ((new16 >> i) & 1u) ? dist : 0.0f);                // range.rs:129, set order
-            idx2 += idx << (2 * i);
+            error = add(error, p.w > 0.0f ? dist : 0.0f);                        // range.rs:129, set order
+            idx2 |= idx << (2 * i);
         }
         if (error < best_error) {                                                  // range.rs:133
             best_error = error;
-            const uint32_t word = (idx2 & (spread16(active16) * 3u)) | inact;
+            const uint32_t word = (idx2 & act2) | inact;
             block = three ? write3_packed(a565, b565, word) : write4_packed(a565, b565, word);
         }
     }
@@ -278,9 +282,13 @@ __device__ __forceinline__ uint2 range_colour_thread(uint32_t px[16], const uint
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------------------
+#ifndef TXP_RANGE_MIN_CTAS
+#define TXP_RANGE_MIN_CTAS 6         // 6 CTAs x 33 KB of shared memory, 24 warps per SM
+#endif
 template <int FMT>
-__global__ void __launch_bounds__(128) range_encode_kernel(const BlockSource src, const EncodeParams prm, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(ROLL_THREADS, TXP_RANGE_MIN_CTAS) range_encode_kernel(const BlockSource src, const EncodeParams prm, uint8_t* __restrict__ out) {
     __shared__ float lut[256];
+    __shared__ float4 s_col[16][ROLL_THREADS];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = fdiv((float)i, 255.0f);   // colourset.rs:65-67
     __syncthreads();
     const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(128) range_encode_kernel(const BlockSource src
         for (int i = 0; i < 16; ++i) v[i] = px[i] >> 24;
         alpha_half = mask == 0xFFFFu ? alpha_fit_full(v) : alpha_fit_thread(v, mask);
     }
-    const uint2 colour = range_colour_thread<FMT == BC1>(px, mask, prm, lut);
+    const uint2 colour = range_colour_rolled<FMT == BC1>(px, mask, prm, lut, &s_col[0][threadIdx.x]);
     if (FMT == BC1) reinterpret_cast<uint2*>(out)[b] = colour;
     else reinterpret_cast<uint4*>(out)[b] = make_uint4(alpha_half.x, alpha_half.y, colour.x, colour.y);
 }
