@@ -231,53 +231,55 @@ __device__ __forceinline__ uint2 range_colour_rolled(uint32_t px[16], const uint
     const uint32_t act2 = spread16(active16) * 3u, inact = spread16(~active16 & 0xFFFFu) * 3u;   // colourset.rs:134-137
 
     // ---- compress3 / compress4 (range.rs:103-192, colourfit.rs:48-59) -------------------------------------------
+    // Both codebooks start with (start, end): the two passes share those distances, so one loop over the pixels evaluates
+    // five codes instead of 3 + 4 (same operations on the same operands => the same bits as the reference's two loops).
+    const bool do3 = IS_BC1, do4 = !(IS_BC1 && ts.transparent);
+    float m3[3], t4a[3], t4b[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        m3[c] = add(mul(sv[c], 0.5f), mul(ev[c], 0.5f));                           // range.rs:161
+        t4a[c] = add(mul(sv[c], 2.0f / 3.0f), mul(ev[c], 1.0f / 3.0f));           // range.rs:179
+        t4b[c] = add(mul(sv[c], 1.0f / 3.0f), mul(ev[c], 2.0f / 3.0f));           // range.rs:180
+    }
+    float err3 = 0.0f, err4 = 0.0f;
+    uint32_t idx3 = 0, idx4 = 0;
+#pragma unroll 2
+    for (int i = 0; i < 16; ++i) {
+        const float4 p = col[i * ROLL_THREADS];
+        // weights are applied before squaring (range.rs:117); the first minimum wins (range.rs:118, strict <)
+        float dx = mul(wx, sub(p.x, sv[0])), dy = mul(wy, sub(p.y, sv[1])), dz = mul(wz, sub(p.z, sv[2]));
+        const float d0 = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+        dx = mul(wx, sub(p.x, ev[0])); dy = mul(wy, sub(p.y, ev[1])); dz = mul(wz, sub(p.z, ev[2]));
+        const float d1 = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+        float dist = d0;
+        uint32_t idx = 0;
+        if (d1 < dist) { dist = d1; idx = 1u; }
+        const bool is_new = p.w > 0.0f;
+        if (IS_BC1) {
+            dx = mul(wx, sub(p.x, m3[0])); dy = mul(wy, sub(p.y, m3[1])); dz = mul(wz, sub(p.z, m3[2]));
+            const float d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+            float dist3 = dist;
+            uint32_t i3 = idx;
+            if (d < dist3) { dist3 = d; i3 = 2u; }
+            err3 = add(err3, is_new ? dist3 : 0.0f);                                // range.rs:129, set order
+            idx3 |= i3 << (2 * i);
+        }
+        dx = mul(wx, sub(p.x, t4a[0])); dy = mul(wy, sub(p.y, t4a[1])); dz = mul(wz, sub(p.z, t4a[2]));
+        float d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+        if (d < dist) { dist = d; idx = 2u; }
+        dx = mul(wx, sub(p.x, t4b[0])); dy = mul(wy, sub(p.y, t4b[1])); dz = mul(wz, sub(p.z, t4b[2]));
+        d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+        if (d < dist) { dist = d; idx = 3u; }
+        err4 = add(err4, is_new ? dist : 0.0f);
+        idx4 |= idx << (2 * i);
+    }
     float best_error = FLT_MAX;
     uint2 block = make_uint2(0u, 0u);
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool three = pass == 0;
-        if (three && !IS_BC1) continue;
-        if (!three && IS_BC1 && ts.transparent) continue;
-        float c2[3], c3[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (three) {
-                c2[c] = add(mul(sv[c], 0.5f), mul(ev[c], 0.5f));
-                c3[c] = 0.f;
-            } else {
-                c2[c] = add(mul(sv[c], 2.0f / 3.0f), mul(ev[c], 1.0f / 3.0f));
-                c3[c] = add(mul(sv[c], 1.0f / 3.0f), mul(ev[c], 2.0f / 3.0f));
-            }
-        }
-        float error = 0.0f;
-        uint32_t idx2 = 0;
-#pragma unroll 2
-        for (int i = 0; i < 16; ++i) {
-            const float4 p = col[i * ROLL_THREADS];
-            // weights are applied before squaring (range.rs:117); the first minimum wins (range.rs:118, strict <)
-            float dx = mul(wx, sub(p.x, sv[0])), dy = mul(wy, sub(p.y, sv[1])), dz = mul(wz, sub(p.z, sv[2]));
-            float dist = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
-            uint32_t idx = 0;
-            dx = mul(wx, sub(p.x, ev[0])); dy = mul(wy, sub(p.y, ev[1])); dz = mul(wz, sub(p.z, ev[2]));
-            float d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
-            if (d < dist) { dist = d; idx = 1u; }
-            dx = mul(wx, sub(p.x, c2[0])); dy = mul(wy, sub(p.y, c2[1])); dz = mul(wz, sub(p.z, c2[2]));
-            d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
-            if (d < dist) { dist = d; idx = 2u; }
-            if (!three) {
-                dx = mul(wx, sub(p.x, c3[0])); dy = mul(wy, sub(p.y, c3[1])); dz = mul(wz, sub(p.z, c3[2]));
-                d = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
-                if (d < dist) { dist = d; idx = 3u; }
-            }
-            error = add(error, p.w > 0.0f ? dist : 0.0f);                        // range.rs:129, set order
-            idx2 |= idx << (2 * i);
-        }
-        if (error < best_error) {                                                  // range.rs:133
-            best_error = error;
-            const uint32_t word = (idx2 & act2) | inact;
-            block = three ? write3_packed(a565, b565, word) : write4_packed(a565, b565, word);
-        }
+    if (do3 && err3 < best_error) {                                                // range.rs:133
+        best_error = err3;
+        block = write3_packed(a565, b565, (idx3 & act2) | inact);
     }
+    if (do4 && err4 < best_error) block = write4_packed(a565, b565, (idx4 & act2) | inact);
     return block;
 }
 
