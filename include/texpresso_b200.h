@@ -109,7 +109,8 @@ TXP_API int txp_decompress_device(int format, const void* d_data, size_t width, 
 /* Balanced block-row range [*row_begin, *row_end) of shard `rank` out of `world` for an image of `height`. */
 TXP_API void txp_shard_rows(size_t height, int rank, int world, size_t* row_begin, size_t* row_end);
 
-/* One process, n_gpus devices (0..n_gpus-1): block rows are split with txp_shard_rows, one host worker
+/* One process, n_gpus devices (0..n_gpus-1; n_gpus == 1 means the calling thread's current device, so that one process per GPU
+ * can use the multi / batch entry points as they are): block rows are split with txp_shard_rows, one host worker
  * per device, each device writes its own slice of `output`.  No collectives. */
 TXP_API int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len, size_t width, size_t height,
                                const txp_params* params, uint8_t* output, size_t output_len, int n_gpus);

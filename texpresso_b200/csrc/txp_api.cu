@@ -133,6 +133,90 @@ __global__ void __launch_bounds__(256) mip_downsample_kernel(const uint32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The whole mip chain of a group of textures in ONE launch (same filter as mip_downsample_kernel, level by level).
+// A CTA owns a 64x64 tile of level 0 of one texture and produces the tile's share of levels 1..6 out of shared memory (a level-l
+// pixel (x, y) only needs level l-1 pixels (2x..2x+1, 2y..2y+1): tiles stay self-contained); the CTA that finishes last for
+// its texture (ticket counter, self-resetting) produces the remaining levels from level 6, which is at most 64x64 pixels for
+// textures up to 4096^2.  One launch instead of ten per texture, for any number of textures of one shape.
+// ---------------------------------------------------------------------------------------------------
+struct MipTable { uint32_t lw[16], lh[16], loff[16]; int nlevels; uint32_t tex_px, tiles_x, tiles; };
+
+__device__ __forceinline__ uint32_t mip_avg4(const uint32_t a, const uint32_t b, const uint32_t c, const uint32_t d) {
+    const uint32_t m = 0x00FF00FFu;
+    const uint32_t even = (((a & m) + (b & m) + (c & m) + (d & m) + 0x00020002u) >> 2) & m;
+    const uint32_t odd = ((((a >> 8) & m) + ((b >> 8) & m) + ((c >> 8) & m) + ((d >> 8) & m) + 0x00020002u) >> 2) & m;
+    return even | (odd << 8);
+}
+
+__global__ void __launch_bounds__(256) mip_chain_kernel(uint32_t* __restrict__ base, const __grid_constant__ MipTable mt, uint32_t* __restrict__ tickets) {
+    __shared__ uint32_t sa[64 * 64], sb[32 * 32];              // level l / level l+1 of the tile; tail: level 6 of the texture (<= 64x64) / level 7
+    __shared__ uint32_t s_last;
+    uint32_t* tex = base + (size_t)blockIdx.y * mt.tex_px;
+    const uint32_t tx = blockIdx.x % mt.tiles_x, ty = blockIdx.x / mt.tiles_x;
+    const int tid = threadIdx.x;
+    // ---- levels 1 .. min(6, nlevels - 1): from global (level 0) resp. shared memory
+    const int in_tile = mt.nlevels - 1 < 6 ? mt.nlevels - 1 : 6;
+    uint32_t* src_s = sa; uint32_t* dst_s = sb;
+    for (int l = 1; l <= in_tile; ++l) {
+        const uint32_t sw = mt.lw[l - 1], sh = mt.lh[l - 1], dw = mt.lw[l], dh = mt.lh[l];
+        const uint32_t ox = (tx * 64) >> l, oy = (ty * 64) >> l, side = 64u >> l;          // this tile's region of level l
+        const uint32_t sox = (tx * 64) >> (l - 1), soy = (ty * 64) >> (l - 1), sside = 64u >> (l - 1);
+        uint32_t* dst_g = tex + mt.loff[l];
+        const uint32_t* src_g = tex + mt.loff[l - 1];
+        for (uint32_t i = tid; i < side * side; i += 256) {
+            const uint32_t lx = i % side, ly = i / side, x = ox + lx, y = oy + ly;
+            if (x < dw && y < dh) {
+                const uint32_t x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+                uint32_t a, b, c, d;
+                if (l == 1) {
+                    a = __ldg(src_g + (size_t)y0 * sw + x0); b = __ldg(src_g + (size_t)y0 * sw + x1);
+                    c = __ldg(src_g + (size_t)y1 * sw + x0); d = __ldg(src_g + (size_t)y1 * sw + x1);
+                } else {
+                    a = src_s[(y0 - soy) * sside + (x0 - sox)]; b = src_s[(y0 - soy) * sside + (x1 - sox)];
+                    c = src_s[(y1 - soy) * sside + (x0 - sox)]; d = src_s[(y1 - soy) * sside + (x1 - sox)];
+                }
+                const uint32_t v = mip_avg4(a, b, c, d);
+                dst_s[ly * side + lx] = v;
+                dst_g[(size_t)y * dw + x] = v;
+            }
+        }
+        __syncthreads();
+        uint32_t* t = src_s; src_s = dst_s; dst_s = t;
+    }
+    if (mt.nlevels - 1 <= 6) return;
+    // ---- the remaining levels, by the CTA that finishes last for this texture
+    __threadfence();
+    if (tid == 0) {
+        const uint32_t ticket = atomicAdd(tickets + blockIdx.y, 1u);
+        s_last = ticket == mt.tiles - 1;
+        if (s_last) tickets[blockIdx.y] = 0;                   // ready for the next launch on this slot
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        const uint32_t w6 = mt.lw[6], h6 = mt.lh[6];
+        const uint32_t* g6 = tex + mt.loff[6];
+        for (uint32_t i = tid; i < w6 * h6; i += 256) sa[i] = __ldcg(g6 + i);      // written by other CTAs: read through L2
+        __syncthreads();
+    }
+    src_s = sa; dst_s = sb;
+    for (int l = 7; l < mt.nlevels; ++l) {
+        const uint32_t sw = mt.lw[l - 1], sh = mt.lh[l - 1], dw = mt.lw[l], dh = mt.lh[l];
+        uint32_t* dst_g = tex + mt.loff[l];
+        for (uint32_t i = tid; i < dw * dh; i += 256) {
+            const uint32_t x = i % dw, y = i / dw;
+            const uint32_t x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+            const uint32_t v = mip_avg4(src_s[y0 * sw + x0], src_s[y0 * sw + x1], src_s[y1 * sw + x0], src_s[y1 * sw + x1]);
+            dst_s[i] = v;
+            dst_g[i] = v;
+        }
+        __syncthreads();
+        uint32_t* t = src_s; src_s = dst_s; dst_s = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Channel expansion to RGBA8 on the device (the reference's CLI does this on the host before Format::compress,
 // cli/src/image/png.rs:47-62, jpeg.rs:42-52): L8 -> (l, l, l, 255), LA8 -> (l, l, l, a), RGB8 -> (r, g, b, 255).
 // One thread per pixel; a warp reads 32..96 contiguous bytes and writes 128.
@@ -239,8 +323,13 @@ struct Slot {
     // deferred copy of a staged result into a pageable caller buffer
     uint8_t* user_out = nullptr;
     size_t user_out_bytes = 0;
+    // the same for texture groups (one entry per texture: destination, offset inside h_out, bytes)
+    struct Deferred { uint8_t* dst; size_t off, n; };
+    std::vector<Deferred> deferred;
+    uint32_t* d_tickets = nullptr;      // mip_chain_kernel: one self-resetting counter per texture of a group
     bool busy = false;
 };
+constexpr int GROUP_MAX = 16;           // textures per group launch
 
 struct DeviceCtx {
     std::mutex mu;
@@ -505,10 +594,10 @@ static int launch_encode(DeviceCtx& ctx, int format, const BlockSource& src, con
         const uint32_t need = (ntiles + (T) / 32 - 1) / ((T) / 32), cap = (uint32_t)ctx.sm_count * (M);               \
         const uint32_t grid = need < cap ? need : cap;                                                                \
         TmaDesc tmap;                                                                                                 \
-        if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged && alpha_tma && (src.bw % 32) == 0 && src.h >= 4 && make_strip_tensor_map(src, &tmap)) { \
+        if (!src.masks && src.nlevels <= 1 && src.ntex <= 1 && src.vec_ok && alpha_staged && alpha_tma && (src.bw % 32) == 0 && src.h >= 4 && make_strip_tensor_map(src, &tmap)) { \
             /* strips of 32 blocks staged with one cp.async.bulk.tensor each (TMA) */                                 \
             alpha_lattice_tma_kernel<F, T, M, LATTICE_STAGES><<<grid, T, lattice_tma_smem<T, LATTICE_STAGES>(), st>>>(tmap, src, d_out, ntiles); \
-        } else if (!src.masks && src.nlevels <= 1 && src.vec_ok && alpha_staged && (uint64_t)src.w * src.h * 4 < 0xF0000000ull) {                                           \
+        } else if (!src.masks && src.nlevels <= 1 && src.ntex <= 1 && src.vec_ok && alpha_staged && (uint64_t)src.w * src.h * 4 < 0xF0000000ull) {                                           \
             /* plain aligned image: cp.async-staged kernel; per-iteration block stride as (quotient, remainder) of bw */ \
             const uint64_t step = (uint64_t)grid * ((T) / 32) * 32;                                                   \
             alpha_lattice_image_kernel<F, T, M, LATTICE_STAGES><<<grid, T, lattice_image_smem<T, LATTICE_STAGES>(), st>>>(             \
@@ -607,6 +696,7 @@ static BlockSource image_source(const uint8_t* d_rgba, size_t w, size_t h, uint6
     s.w = (uint32_t)w; s.h = (uint32_t)h; s.bw = (uint32_t)((w + 3) / 4);
     s.nblocks = nblocks;
     s.nlevels = 1;
+    s.ntex = 1; s.tex_px = 0; s.tex_blocks = 0;
     s.vec_ok = ((w % 4) == 0 && (reinterpret_cast<uintptr_t>(d_rgba) % 16) == 0) ? 1 : 0;
     return s;
 }
@@ -622,6 +712,8 @@ static int slot_wait(Slot& s) {
     if (!s.busy) return TXP_OK;
     TXP_CUDA(cudaEventSynchronize(s.done));
     if (s.user_out) { std::memcpy(s.user_out, s.h_out, s.user_out_bytes); s.user_out = nullptr; }
+    for (const Slot::Deferred& d : s.deferred) std::memcpy(d.dst, s.h_out + d.off, d.n);
+    s.deferred.clear();
     s.busy = false;
     return TXP_OK;
 }
@@ -637,7 +729,7 @@ static int slot_wait(Slot& s) {
 static void slots_abandon(DeviceCtx& c) {
     for (Slot& s : c.slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        s.user_out = nullptr; s.user_out_bytes = 0; s.busy = false;
+        s.user_out = nullptr; s.user_out_bytes = 0; s.deferred.clear(); s.busy = false;
     }
     cudaGetLastError();
 }
@@ -856,6 +948,11 @@ static int compress_checked(int format, const uint8_t* rgba, size_t rgba_len, si
 }
 
 
+// Device driven by worker g of a multi-device call over n_gpus devices: devices 0 .. n_gpus - 1, except that a call with
+// n_gpus == 1 stays on the calling thread's CURRENT device (one process per GPU under torchrun: every rank passes n_gpus = 1
+// after txp_set_device(local_rank)).
+static int worker_device(const int g, const int n_gpus, const int caller_device) { return n_gpus == 1 ? caller_device : g; }
+
 // ---- mip chains (extension; SURVEY 8(f) row 4 / BASELINE config 5) -------------------------------------------------
 static int mip_layout(int format, size_t w, size_t h, BlockSource* src, size_t* total_px, size_t* total_out) {
     int n = 0; size_t px = 0; uint64_t blocks = 0;
@@ -875,10 +972,11 @@ static int mip_layout(int format, size_t w, size_t h, BlockSource* src, size_t* 
     return n;
 }
 
-// enqueue H2D(level 0) -> mip kernels -> one encode launch -> D2H on slot s; the caller waits on the slot
-// with_mips = false: level 0 only (a whole texture per slot: txp_compress_batch)
-static int mipchain_enqueue_impl(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
-                                 const bool concurrent, const bool with_mips) {
+// Enqueue a GROUP of k textures of one shape on slot s: k H2D copies (level 0) -> one mip-chain launch -> ONE encode launch over
+// all levels of all textures -> k D2H copies; the caller waits on the slot.  with_mips = false: level 0 only (txp_compress_batch).
+// concurrent: other slots are in flight too (lets a small launch take the lane-per-block search, see launch_encode).
+static int group_enqueue_impl(DeviceCtx& ctx, Slot& s, int format, const uint8_t* const* rgba, const int k, size_t w, size_t h, const txp_params* p,
+                              uint8_t* const* outputs, const bool concurrent, const bool with_mips) {
     BlockSource src;
     size_t total_px = 0, total_out = 0;
     int n = 1;
@@ -889,37 +987,68 @@ static int mipchain_enqueue_impl(DeviceCtx& ctx, Slot& s, int format, const uint
         total_px = w * h;
         total_out = txp_compressed_size(format, w, h);
     }
+    const size_t tex_px = (total_px + 3) & ~size_t(3);            // textures 16-byte aligned
     int rc;
-    if ((rc = grow_dev(&s.d_in, &s.d_in_cap, total_px * 4)) != TXP_OK) return rc;
-    if ((rc = grow_dev(&s.d_out, &s.d_out_cap, total_out)) != TXP_OK) return rc;
+    if ((rc = grow_dev(&s.d_in, &s.d_in_cap, (size_t)k * tex_px * 4)) != TXP_OK) return rc;
+    if ((rc = grow_dev(&s.d_out, &s.d_out_cap, (size_t)k * total_out)) != TXP_OK) return rc;
     const size_t in_bytes = w * h * 4;
-    const uint8_t* src_ptr = rgba;
-    if (!dma_direct(rgba)) {
-        if ((rc = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) return rc;
-        std::memcpy(s.h_in, rgba, in_bytes);
-        src_ptr = s.h_in;
+    bool staged_in = false;
+    for (int t = 0; t < k; ++t) {
+        const uint8_t* src_ptr = rgba[t];
+        if (!dma_direct(src_ptr)) {
+            if (!staged_in && (rc = grow_pinned(&s.h_in, &s.h_in_cap, (size_t)k * in_bytes)) != TXP_OK) return rc;
+            staged_in = true;
+            std::memcpy(s.h_in + (size_t)t * in_bytes, src_ptr, in_bytes);
+            src_ptr = s.h_in + (size_t)t * in_bytes;
+        }
+        TXP_CUDA(cudaMemcpyAsync(s.d_in + (size_t)t * tex_px * 4, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
     }
-    TXP_CUDA(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
     uint32_t* base = reinterpret_cast<uint32_t*>(s.d_in);
-    for (int l = 1; l < n; ++l) {
-        const uint32_t dw = src.lw[l], dh = src.lh[l];
-        mip_downsample_kernel<<<(dw * dh + 255) / 256, 256, 0, s.stream>>>(base + src.loff[l - 1], src.lw[l - 1], src.lh[l - 1], base + src.loff[l], dw, dh);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (n > 1) {
+        if (src.lw[0] <= 4096 && src.lh[0] <= 4096) {
+            if (!s.d_tickets) {
+                TXP_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.d_tickets), GROUP_MAX * sizeof(uint32_t)));
+                TXP_CUDA(cudaMemsetAsync(s.d_tickets, 0, GROUP_MAX * sizeof(uint32_t), s.stream));
+            }
+            MipTable mt;
+            for (int l = 0; l < 16; ++l) { mt.lw[l] = l < n ? src.lw[l] : 1; mt.lh[l] = l < n ? src.lh[l] : 1; mt.loff[l] = l < n ? src.loff[l] : 0; }
+            mt.nlevels = n; mt.tex_px = (uint32_t)tex_px;
+            mt.tiles_x = (uint32_t)((w + 63) / 64); mt.tiles = mt.tiles_x * (uint32_t)((h + 63) / 64);
+            mip_chain_kernel<<<dim3(mt.tiles, (unsigned)k), 256, 0, s.stream>>>(base, mt, s.d_tickets);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        } else {                                                      // very large textures: one launch per level
+            for (int t = 0; t < k; ++t)
+                for (int l = 1; l < n; ++l) {
+                    const uint32_t dw = src.lw[l], dh = src.lh[l];
+                    uint32_t* tb = base + (size_t)t * tex_px;
+                    mip_downsample_kernel<<<(dw * dh + 255) / 256, 256, 0, s.stream>>>(tb + src.loff[l - 1], src.lw[l - 1], src.lh[l - 1], tb + src.loff[l], dw, dh);
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                }
+        }
+        TXP_CUDA(cudaGetLastError());
     }
-    TXP_CUDA(cudaGetLastError());
+    uint64_t tex_blocks;
     if (with_mips) {
         src.rgba = s.d_in; src.masks = nullptr; src.w = (uint32_t)w; src.h = (uint32_t)h; src.bw = (uint32_t)txp_num_blocks(w);
         src.vec_ok = 1;                                   // cudaMalloc base; per-level width checked in locate_block
+        tex_blocks = src.nblocks;
     } else {
-        src = image_source(s.d_in, w, h, (uint64_t)txp_num_blocks(w) * txp_num_blocks(h));
+        tex_blocks = (uint64_t)txp_num_blocks(w) * txp_num_blocks(h);
+        src = image_source(s.d_in, w, h, tex_blocks);
     }
+    src.ntex = (uint32_t)k; src.tex_px = (uint32_t)tex_px; src.tex_blocks = (uint32_t)tex_blocks;
+    src.nblocks = tex_blocks * (uint64_t)k;
     if ((rc = launch_encode(ctx, format, src, p, s.d_out, s.stream, concurrent)) != TXP_OK) return rc;
-    if (dma_direct(output)) {
-        TXP_CUDA(cudaMemcpyAsync(output, s.d_out, total_out, cudaMemcpyDefault, s.stream));
-    } else {
-        if ((rc = grow_pinned(&s.h_out, &s.h_out_cap, total_out)) != TXP_OK) return rc;
-        TXP_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, total_out, cudaMemcpyDeviceToHost, s.stream));
-        s.user_out = output; s.user_out_bytes = total_out;
+    bool staged_out = false;
+    for (int t = 0; t < k; ++t) {
+        if (dma_direct(outputs[t])) {
+            TXP_CUDA(cudaMemcpyAsync(outputs[t], s.d_out + (size_t)t * total_out, total_out, cudaMemcpyDefault, s.stream));
+        } else {
+            if (!staged_out && (rc = grow_pinned(&s.h_out, &s.h_out_cap, (size_t)k * total_out)) != TXP_OK) return rc;
+            staged_out = true;
+            TXP_CUDA(cudaMemcpyAsync(s.h_out + (size_t)t * total_out, s.d_out + (size_t)t * total_out, total_out, cudaMemcpyDeviceToHost, s.stream));
+            s.deferred.push_back({outputs[t], (size_t)t * total_out, total_out});
+        }
     }
     TXP_CUDA(cudaEventRecord(s.done, s.stream));
     s.busy = true;
@@ -927,16 +1056,34 @@ static int mipchain_enqueue_impl(DeviceCtx& ctx, Slot& s, int format, const uint
 }
 
 // a failure after the first asynchronous operation must not leave work in flight on a slot that is not marked busy
-static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
-                            const bool concurrent = false, const bool with_mips = true) {
-    const int rc = mipchain_enqueue_impl(ctx, s, format, rgba, w, h, p, output, concurrent, with_mips);
+static int group_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* const* rgba, const int k, size_t w, size_t h, const txp_params* p,
+                         uint8_t* const* outputs, const bool concurrent, const bool with_mips) {
+    const int rc = group_enqueue_impl(ctx, s, format, rgba, k, w, h, p, outputs, concurrent, with_mips);
     if (rc != TXP_OK) {
         const std::string keep = t_last_error;
         cudaStreamSynchronize(s.stream); cudaGetLastError();
-        s.user_out = nullptr; s.user_out_bytes = 0; s.busy = false;
+        s.user_out = nullptr; s.user_out_bytes = 0; s.deferred.clear(); s.busy = false;
         t_last_error = keep;
     }
     return rc;
+}
+
+static int mipchain_enqueue(DeviceCtx& ctx, Slot& s, int format, const uint8_t* rgba, size_t w, size_t h, const txp_params* p, uint8_t* output,
+                            const bool concurrent = false, const bool with_mips = true) {
+    return group_enqueue(ctx, s, format, &rgba, 1, w, h, p, &output, concurrent, with_mips);
+}
+
+// Textures of this worker (t = first, first + stride, ...) from index `from`: how many consecutive ones share the shape of
+// texture `from` and fit one group (<= GROUP_MAX textures, <= GROUP_BYTES of pixels)
+constexpr size_t GROUP_BYTES = 48u << 20;
+static int group_extent(const size_t* widths, const size_t* heights, size_t n_textures, size_t from, size_t stride, size_t bytes_per_texture) {
+    int k = 1;
+    size_t bytes = bytes_per_texture;
+    for (size_t t = from + stride; t < n_textures && k < GROUP_MAX; t += stride) {
+        if (widths[t] != widths[from] || heights[t] != heights[from] || bytes + bytes_per_texture > GROUP_BYTES) break;
+        ++k; bytes += bytes_per_texture;
+    }
+    return k;
 }
 
 }  // namespace txp
@@ -1135,7 +1282,7 @@ int txp_compress_blocks(int format, const uint8_t* rgba_blocks, const uint32_t* 
     TXP_CUDA(cudaMemcpyAsync(s.d_in, rgba_blocks, n * 64, cudaMemcpyDefault, s.stream));
     TXP_CUDA(cudaMemcpyAsync(c->d_masks, masks, n * 4, cudaMemcpyDefault, s.stream));
     BlockSource src;
-    src.rgba = s.d_in; src.masks = c->d_masks; src.w = 0; src.h = 0; src.bw = 1; src.nblocks = n; src.vec_ok = 1; src.nlevels = 1;
+    src.rgba = s.d_in; src.masks = c->d_masks; src.w = 0; src.h = 0; src.bw = 1; src.nblocks = n; src.vec_ok = 1; src.nlevels = 1; src.ntex = 1; src.tex_px = 0; src.tex_blocks = 0;
     if ((rc = launch_encode(*c, format, src, params, s.d_out, s.stream)) != TXP_OK) return rc;
     TXP_CUDA(cudaMemcpyAsync(output, s.d_out, n * bs, cudaMemcpyDefault, s.stream));
     TXP_CUDA(cudaStreamSynchronize(s.stream));
@@ -1213,6 +1360,8 @@ int txp_compress_batch_mips(int format, const uint8_t* const* rgba, const size_t
     if (!rgba || !widths || !heights || !outputs) return fail(TXP_ERR_ARGUMENT, "null pointer");
     const int ndev = txp_device_count();
     if (ndev < 0) return ndev;
+    int caller_device = 0;
+    TXP_CUDA(cudaGetDevice(&caller_device));
     if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
     for (size_t t = 0; t < n_textures; ++t)
         if (widths[t] == 0 || heights[t] == 0 || widths[t] > 0x3FFFFFFFull || heights[t] > 0x3FFFFFFFull)
@@ -1224,16 +1373,25 @@ int txp_compress_batch_mips(int format, const uint8_t* const* rgba, const size_t
         workers.emplace_back([&, g]() {
             int r = TXP_OK;
             DeviceCtx* c = nullptr;
-            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
-            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            const int dev = worker_device(g, n_gpus, caller_device);
+            if (cudaSetDevice(dev) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(dev, &c);
             if (r == TXP_OK) {
                 std::lock_guard<std::mutex> lk(c->mu);
                 size_t k = 0;                              // texture t -> device t % n_gpus, slots round-robin so that
-                for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus, ++k) {   // copies overlap kernels
+                for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; ++k) {   // copies overlap kernels
+                    // consecutive textures of one shape share one mip-chain launch and one encode launch
+                    const int ng = group_extent(widths, heights, n_textures, t, (size_t)n_gpus, widths[t] * heights[t] * 16 / 3 + 64);
+                    const uint8_t* ins[GROUP_MAX]; uint8_t* outs[GROUP_MAX];
+                    for (int i = 0; i < ng; ++i) {
+                        ins[i] = rgba[t + (size_t)i * n_gpus]; outs[i] = outputs[t + (size_t)i * n_gpus];
+                        if (!ins[i] || !outs[i]) r = fail(TXP_ERR_ARGUMENT, "null texture pointer");
+                    }
+                    if (r != TXP_OK) break;
                     Slot& s = c->slots[k % NSLOTS];
-                    if (!rgba[t] || !outputs[t]) { r = fail(TXP_ERR_ARGUMENT, "null texture pointer"); break; }
                     if ((r = slot_wait(s)) != TXP_OK) break;
-                    r = mipchain_enqueue(*c, s, format, rgba[t], widths[t], heights[t], params, outputs[t], true);
+                    r = group_enqueue(*c, s, format, ins, ng, widths[t], heights[t], params, outs, true, true);
+                    t += (size_t)ng * n_gpus;
                 }
                 for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
             }
@@ -1253,6 +1411,8 @@ int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len, size_t 
     if ((rc = compress_checked(format, rgba, rgba_len, width, height, params, output, output_len)) != TXP_OK) return rc;
     const int ndev = txp_device_count();
     if (ndev < 0) return ndev;
+    int caller_device = 0;
+    TXP_CUDA(cudaGetDevice(&caller_device));
     if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
     const size_t bs = (size_t)block_bytes(format), bw = txp_num_blocks(width);
     const uint64_t nblocks = output_len / bs;
@@ -1266,8 +1426,9 @@ int txp_compress_multi(int format, const uint8_t* rgba, size_t rgba_len, size_t 
             if (r0 >= r1) return;
             int r = TXP_OK;
             DeviceCtx* c = nullptr;
-            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
-            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            const int dev = worker_device(g, n_gpus, caller_device);
+            if (cudaSetDevice(dev) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(dev, &c);
             if (r == TXP_OK) {
                 uint64_t nb = (uint64_t)(r1 - r0) * bw;
                 const uint64_t first = (uint64_t)r0 * bw;
@@ -1293,6 +1454,8 @@ int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* wid
     if (!rgba || !widths || !heights || !outputs) return fail(TXP_ERR_ARGUMENT, "null pointer");
     const int ndev = txp_device_count();
     if (ndev < 0) return ndev;
+    int caller_device = 0;
+    TXP_CUDA(cudaGetDevice(&caller_device));
     if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
     std::vector<int> rcs((size_t)n_gpus, TXP_OK);
     std::vector<std::string> errs((size_t)n_gpus);
@@ -1301,26 +1464,37 @@ int txp_compress_batch(int format, const uint8_t* const* rgba, const size_t* wid
         workers.emplace_back([&, g]() {
             int r = TXP_OK;
             DeviceCtx* c = nullptr;
-            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
-            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            const int dev = worker_device(g, n_gpus, caller_device);
+            if (cudaSetDevice(dev) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(dev, &c);
             if (r == TXP_OK) {
                 std::lock_guard<std::mutex> lk(c->mu);
                 size_t k = 0;
-                for (size_t t = (size_t)g; t < n_textures && r == TXP_OK; t += (size_t)n_gpus) {
+                for (size_t t = (size_t)g; t < n_textures && r == TXP_OK;) {
                     const size_t w = widths[t], h = heights[t];
                     if ((r = check_dims(w, h)) != TXP_OK) break;
                     if (!rgba[t] || !outputs[t]) { r = fail(TXP_ERR_ARGUMENT, "null texture pointer"); break; }
                     if (h != 0 && w * h * 4 <= CHUNK_BYTES) {
-                        // a whole texture per pipeline slot: copies and kernels of neighbouring textures overlap
+                        // whole textures per pipeline slot (copies and kernels of neighbouring slots overlap); consecutive textures
+                        // of one shape share one encode launch
+                        const int ng = group_extent(widths, heights, n_textures, t, (size_t)n_gpus, w * h * 4);
+                        const uint8_t* ins[GROUP_MAX]; uint8_t* outs[GROUP_MAX];
+                        for (int i = 0; i < ng; ++i) {
+                            ins[i] = rgba[t + (size_t)i * n_gpus]; outs[i] = outputs[t + (size_t)i * n_gpus];
+                            if (!ins[i] || !outs[i]) r = fail(TXP_ERR_ARGUMENT, "null texture pointer");
+                        }
+                        if (r != TXP_OK) break;
                         Slot& s = c->slots[k++ % NSLOTS];
                         if ((r = slot_wait(s)) != TXP_OK) break;
-                        r = mipchain_enqueue(*c, s, format, rgba[t], w, h, params, outputs[t], true, false);
+                        r = group_enqueue(*c, s, format, ins, ng, w, h, params, outs, true, false);
+                        t += (size_t)ng * n_gpus;
                     } else {
                         // large texture: the chunked pipeline of txp_compress (it drains the slots itself at the end)
                         for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
                         if (r != TXP_OK) break;
                         const size_t bw = txp_num_blocks(w), rows = txp_num_blocks(h);
                         r = compress_host_rows(*c, format, rgba[t], w, h, params, outputs[t], 0, rows, (uint64_t)bw * rows);
+                        t += (size_t)n_gpus;
                     }
                 }
                 for (Slot& s : c->slots) { const int r2 = slot_wait(s); if (r == TXP_OK) r = r2; }
@@ -1341,6 +1515,8 @@ int txp_decompress_multi(int format, const uint8_t* data, size_t data_len, size_
     if ((rc = decompress_checked(format, data, data_len, width, height, output, output_len)) != TXP_OK) return rc;
     const int ndev = txp_device_count();
     if (ndev < 0) return ndev;
+    int caller_device = 0;
+    TXP_CUDA(cudaGetDevice(&caller_device));
     if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
     if (width * height == 0) return TXP_OK;
     const size_t bs = (size_t)block_bytes(format), bw = txp_num_blocks(width), rows = txp_num_blocks(height);
@@ -1353,8 +1529,9 @@ int txp_decompress_multi(int format, const uint8_t* data, size_t data_len, size_
             if (r0 >= r1) return;
             int r = TXP_OK;
             DeviceCtx* c = nullptr;
-            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
-            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            const int dev = worker_device(g, n_gpus, caller_device);
+            if (cudaSetDevice(dev) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(dev, &c);
             if (r == TXP_OK) {
                 std::lock_guard<std::mutex> lk(c->mu);
                 r = decompress_host_rows(*c, format, data + r0 * bw * bs, width, height, output + 4 * r0 * width * 4, r0, r1);
@@ -1376,6 +1553,8 @@ int txp_decompress_batch(int format, const uint8_t* const* data, const size_t* w
     if (!data || !widths || !heights || !outputs) return fail(TXP_ERR_ARGUMENT, "null pointer");
     const int ndev = txp_device_count();
     if (ndev < 0) return ndev;
+    int caller_device = 0;
+    TXP_CUDA(cudaGetDevice(&caller_device));
     if (n_gpus < 1 || n_gpus > ndev) return fail(TXP_ERR_ARGUMENT, "n_gpus must be between 1 and the device count");
     std::vector<int> rcs((size_t)n_gpus, TXP_OK);
     std::vector<std::string> errs((size_t)n_gpus);
@@ -1384,8 +1563,9 @@ int txp_decompress_batch(int format, const uint8_t* const* data, const size_t* w
         workers.emplace_back([&, g]() {
             int r = TXP_OK;
             DeviceCtx* c = nullptr;
-            if (cudaSetDevice(g) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
-            if (r == TXP_OK) r = ensure_ctx(g, &c);
+            const int dev = worker_device(g, n_gpus, caller_device);
+            if (cudaSetDevice(dev) != cudaSuccess) r = fail(TXP_ERR_CUDA, "cudaSetDevice failed");
+            if (r == TXP_OK) r = ensure_ctx(dev, &c);
             if (r == TXP_OK) {
                 std::lock_guard<std::mutex> lk(c->mu);
                 size_t k = 0;
