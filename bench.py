@@ -28,10 +28,10 @@ FLOPS_BC1 = 151 * 138 + 967 * 159
 UNIT = "Mpix/s"
 # from the ncu --set full capture of the BC3 launch pair (profiles/, per round): FMA-pipe utilisation of cluster_lane_kernel<BC3> and
 # DRAM bytes (read + write) of setup + search for one 8192^2 launch
-NCU_FMA_PIPE_FRAC = 0.801
-NCU_FMA_PIPE_SOURCE = "ncu sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active of cluster_lane_kernel<BC3>, profiles/ncu_lane_r01_summary.txt"
-NCU_TRAFFIC_BYTES_8192 = 2859.4e6
-NCU_TRAFFIC_SOURCE = "profiles/ncu_lane_r01_summary.txt: setup 335.7 MB + 1204 MB, search 1254 MB + 65.3 MB (292 B/block of scratch between the two kernels)"
+NCU_FMA_PIPE_FRAC = 0.807
+NCU_FMA_PIPE_SOURCE = "ncu sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active of cluster_lane_kernel<BC3>, profiles/ncu_lane_r02_summary.txt"
+NCU_TRAFFIC_BYTES_8192 = 1389.6e6
+NCU_TRAFFIC_SOURCE = "profiles/ncu_setup_r02_summary.txt + ncu_lane_r02_summary.txt (dram read + write): setup 378.3 MB + 472.6 MB, search 476.1 MB + 62.6 MB (96-byte point records + 16-byte block records of scratch between the two kernels)"
 METRIC = "BC1/BC3 ClusterFit Mpix/s (8192^2 synthetic RGBA)"
 
 

@@ -49,6 +49,9 @@ __device__ uint4 g_alpha_lattice[512];            // TXP_ALPHA_LATTICE (alpha_la
 #define TXP_LAT_MM 0       // min / max: 0 = VIMNMX3 trees, 1 = two-input VIMNMX
 #endif
 
+#ifndef TXP_LAT_PACK
+#define TXP_LAT_PACK 0     // index bytes -> 48-bit field: 0 = shift / or / mask (ALU pipe), 1 = multiply-gather (IMAD with immediates, FMA pipe) + masks
+#endif
 #ifndef TXP_LAT_LIFT
 #define TXP_LAT_LIFT 1     // regular path, pixel -> fp32: 1 = IDP.4A (FMA pipe): 1.5*2^16 + v with the byte at mantissa bits 7..14; 0 = PRMT (ALU pipe): 1.5*2^15 + v, bits 8..15
 #endif
@@ -98,6 +101,24 @@ __device__ __forceinline__ int lattice_book(const uint32_t vm[16], const uint32_
 
 // four byte-sized 3-bit indices per word -> 48-bit index field + end points (alpha.rs:121-144)
 __device__ __forceinline__ uint2 pack_alpha_block(const uint32_t a0, const uint32_t a1, const uint32_t w[4]) {
+#if TXP_LAT_PACK
+    // Multiply-gather: the index bytes (i0, i1, i2, i3) of a word occupy bits 0-2, 8-10, 16-18, 24-26, so w * 33 = w | w << 5 puts
+    // i0 next to i1 (bits 5-10) and i2 next to i3 (bits 21-26); after masking, y * 1025 = y | y << 10 puts the two 6-bit halves
+    // next to each other (bits 15-26 = the 12-bit field z of four pixels).  A further power of two in the second multiplier
+    // places z where the output word wants it, so the only shifts left are the two right shifts.  Products of disjoint bit
+    // patterns: no carries, the multiplications are exact ORs and run on the FMA pipe (IMAD with an immediate).
+    uint32_t y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = (w[k] * 33u) & 0x07E007E0u;
+    const uint32_t u0 = y[0] * (1025u << 1);          // z0 at bits 16-27
+    const uint32_t u1a = y[1] * (1025u << 13);        // low 4 bits of z1 at bits 28-31
+    const uint32_t u1b = (y[1] * 1025u) >> 19;        // z1 >> 4 at bits 0-7 (bit 12: a stray copy, masked below)
+    const uint32_t u2 = ((y[2] * 1025u) & 0x07FF8000u) >> 7;   // z2 at bits 8-19
+    const uint32_t u3 = y[3] * (1025u << 5);          // z3 at bits 20-31
+    const uint32_t x = (u1a & 0xF0000000u) | ((u0 & 0x0FFF0000u) | (a0 | (a1 << 8)));
+    const uint32_t yy = (u3 & 0xFFF00000u) | ((u1b & 0xFFu) | u2);
+    return make_uint2(x, yy);
+#else
     uint32_t z[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -106,6 +127,7 @@ __device__ __forceinline__ uint2 pack_alpha_block(const uint32_t a0, const uint3
     }
     const uint32_t g0 = z[0] | (z[1] << 12), g1 = z[2] | (z[3] << 12);
     return make_uint2(a0 | (a1 << 8) | (g0 << 16), (g0 >> 16) | (g1 << 8));
+#endif
 }
 
 // Flat and narrow-range blocks (what flat regions of real textures are made of), also in closed form:
@@ -143,6 +165,23 @@ __device__ __forceinline__ uint2 alpha_fit_narrow(const uint32_t lo, const uint3
 // packed bytes.  Returns true (out written) for a regular block, false for one that goes to the queue.
 __device__ __forceinline__ bool alpha_fit_lattice(const uint32_t vm[16], const uint32_t V[4], const uint4* __restrict__ tab, uint2& out) {
     // min / max on the raw bits (positive floats order like integers)
+#if TXP_LAT_MM == 2
+    // Both at once: with q = v << 7 (vm = 1.5 * 2^16 + v as bits = MAGIC16 + q) one IMAD (FMA pipe) forms the half-word pair
+    // (q, 32640 - q):  vm * (1 - 2^16) + C = q + ((32640 - q) << 16)  (mod 2^32; MAGIC16 << 16 == 0), and ONE unsigned 16x2 minimum
+    // tree yields min q in the low half and 32640 - max q in the high half: 8 ALU-pipe instructions instead of 16.
+    static_assert(TXP_LAT_LIFT == 1, "TXP_LAT_MM == 2 needs the IDP.4A lift");
+    uint32_t pq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pq[i] = vm[i] * 0xFFFF0001u + ((32640u << 16) - MAGIC16);
+    uint32_t m2 = __vimin3_u16x2(pq[0], pq[1], pq[2]);
+#pragma unroll
+    for (int i = 3; i < 15; i += 2) m2 = __vimin3_u16x2(m2, pq[i], pq[i + 1]);
+    m2 = __vminu2(m2, pq[15]);
+    const uint32_t qmin = m2 & 0xFFFFu, hq = m2 >> 16;                 // hq = 32640 - q_max
+    const uint32_t span = 32640u - hq - qmin;
+    if (!(qmin != 0u && hq != 0u && span >= (7u << 7))) return false;
+    const uint32_t mn = MAGIC16 + qmin, mx = (MAGIC16 + 32640u) - hq;
+#else
 #if TXP_LAT_MM
     uint32_t mn = min(vm[0], vm[1]), mx = max(vm[0], vm[1]);
 #pragma unroll
@@ -155,6 +194,7 @@ __device__ __forceinline__ bool alpha_fit_lattice(const uint32_t vm[16], const u
 #endif
     const uint32_t span = mx - mn;                                     // r << LIFT_SHIFT
     if (!(mn > LIFT_MAGIC && mx < (LIFT_MAGIC | (255u << LIFT_SHIFT)) && span >= (7u << LIFT_SHIFT))) return false;
+#endif
 
     const uint4 e5 = tab[span >> (LIFT_SHIFT - 1)], e7 = tab[(span >> (LIFT_SHIFT - 1)) + 1];        // row r = two uint4
     const uint32_t lo = (mn >> LIFT_SHIFT) & 255u, hi = (mx >> LIFT_SHIFT) & 255u;
