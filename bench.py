@@ -219,6 +219,8 @@ def run_ours(args):
 
     # ---- this rank's shard: block rows [r0, r1) -----------------------------------------------------------
     r0, r1 = T.shard_rows(H, rank, world)
+    if args.shard_of > 1 and world == 1:                  # tuning aid: rank 0's shard of an N-rank run on one GPU (values are per shard)
+        r0, r1 = T.shard_rows(H, 0, args.shard_of)
     rows = r1 - r0
     hs = 4 * rows
     img = synth.generate("noise_alpha", W, H, SEED, y0=4 * r0, y1=4 * r1)
@@ -601,6 +603,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` sub-records (the other BASELINE configurations)")
     ap.add_argument("--batch-textures", type=int, default=4096, help="textures of BASELINE config 5 (configs.cfg5_batch_mips_bc3)")
+    ap.add_argument("--shard-of", type=int, default=1, help="tuning aid (N=1 only): time rank 0's block-row shard of an N-rank run")
     ap.add_argument("--workload", default="cluster", choices=["cluster", "iterative"],
                     help="cluster (default, the BASELINE metric): BC1+BC3 ClusterFit; iterative: BASELINE config 3, BC1 IterativeClusterFit")
     args = ap.parse_args()

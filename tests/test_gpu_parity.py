@@ -352,6 +352,37 @@ def test_lane_chunk_rows_round_up(T):
     assert np.array_equal(a[200 * 1500 * 8:208 * 1500 * 8], want)
 
 
+@pytest.mark.parametrize("fmt", [0, 2])
+def test_round_aligned_plan_shard_vs_oracle(T, fmt):
+    """One rank's shard of the metric texture at 8 ranks (8192 x 1024 = 4.6 rounds of the lane-per-block search) through the host API:
+    the round-aligned chunk plan (two small warp-per-block chunks, then lane chunks of whole rounds) gives the bytes of the uniform plan
+    and of the oracle on slices across every chunk boundary; a ragged height (partly masked last block row) takes the same path."""
+    import ctypes
+    from texpresso_b200 import synth, _lib
+    L = _lib.load()
+    w = 8192
+    tp, op = _params(T, 1, O.PERCEPTUAL)
+    bs = 8 if fmt == 0 else 16
+    for h in (1024, 1022):
+        img = synth.generate("noise_opaque" if fmt == 0 else "noise_alpha", w, h, seed=3)
+        lane0, warp0 = _debug_get(2), _debug_get(4)
+        a = T.Format(fmt).compress(img, w, h, tp)
+        lane, warp = _debug_get(2) - lane0, _debug_get(4) - warp0
+        assert lane == 3 and warp == 2, (lane, warp)         # chunks of 8, 27 | 111, 55, 55 block rows
+        _lib.check(L.txp_debug_set(5, 0))
+        try:
+            b = T.Format(fmt).compress(img, w, h, tp)
+        finally:
+            _lib.check(L.txp_debug_set(5, 4))
+        assert np.array_equal(a, b)
+        rowbytes = (w // 4) * bs
+        for r0 in (4, 31, 142, 197, 248):                     # block rows around the chunk boundaries 8, 35, 146, 201 and the end
+            y0, y1 = 4 * r0, min(4 * r0 + 32, h)
+            want = O.compress(fmt, img[y0:y1, 4096:6144], 2048, y1 - y0, op, threads=8).reshape(8, -1)
+            got = a[r0 * rowbytes:(r0 + 8) * rowbytes].reshape(8, rowbytes)[:, 1024 * bs:1536 * bs]
+            assert np.array_equal(got, want), (h, r0)
+
+
 @pytest.mark.parametrize("fmt", range(5))
 def test_decompress_multi_and_batch(T, fmt):
     from texpresso_b200 import synth

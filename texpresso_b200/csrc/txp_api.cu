@@ -288,6 +288,10 @@ static std::atomic<long long> g_lane_min_blocks{[] { const char* v = getenv("TXP
 #endif
 static std::atomic<int> g_chunk_mib{[] { const char* v = getenv("TXP_CHUNK_MIB"); return v ? atoi(v) : 0; }()};   // > 0: pipeline chunk size override (A/B)
 static std::atomic<int> g_plan_growth{[] { const char* v = getenv("TXP_PLAN_GROWTH"); return v ? atoi(v) : 3; }()};   // geometric chunk plan of small ClusterFit shards; <= 1: off
+// round-aligned chunk plan of small ClusterFit shards (pipeline_plan): smallest shard, in rounds of the lane-per-block search, that takes it; 0 = off
+static std::atomic<int> g_wave_plan{[] { const char* v = getenv("TXP_WAVE_PLAN"); return v ? atoi(v) : 4; }()};
+static std::atomic<int> g_wave_plan_max{[] { const char* v = getenv("TXP_WAVE_PLAN_MAX"); return v ? atoi(v) : 20; }()};   // ... and the largest (<= 120 rounds: 64 chunks)
+static std::atomic<int> g_wave_chunk{[] { const char* v = getenv("TXP_WAVE_CHUNK"); return v ? atoi(v) : 2; }()};   // rounds per lane chunk of that plan
 static std::atomic<int> g_hybrid_tail{[] { const char* v = getenv("TXP_HYBRID_TAIL"); return v ? atoi(v) : TXP_TAIL_FRAC; }()};
 constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (292 B of scratch per block)
 
@@ -773,12 +777,62 @@ static size_t pipeline_rows_per_chunk(int format, const txp_params* p, size_t w,
 //  * ClusterFit shards of fewer than three lane-sized chunks (8192^2 over 8 GPUs: 256 block rows per rank): geometric growth
 //    c, G c, rest -- every chunk's kernels cover the next chunk's copy (compute : PCIe time is ~3.6 : 1) and only a small copy
 //    is exposed at either end (profiles/iter_e2e_r02.txt: 2.83 ms instead of 2.86 ms for BC3, 3.12 instead of 3.25 ms for BC1)
-static std::vector<size_t> pipeline_plan(int format, const txp_params* p, size_t w, size_t rows) {
+//  * ClusterFit shards of g_wave_plan..g_wave_plan_max rounds of the lane-per-block search (8192^2 over 8 GPUs: 4.6 rounds per rank):
+//    round-aligned plan.  One lane evaluates its block's 967 candidates back to back, so a lane launch costs whole rounds of
+//    `wave` blocks; the shard is cut into lane chunks of exactly two rounds / one round (rounded DOWN to whole block rows; the
+//    single rounds last: the copy of the last chunk's output is the one nothing overlaps) and the remainder -- the part of a round
+//    that would otherwise be a partly filled last round -- goes FIRST, in two small chunks on the warp-per-block search, which is
+//    the right structure for a launch that is alone on the GPU while the larger copies are still in flight.  *lane_chunks: bit i
+//    set = chunk i takes the lane-per-block search although it is below the lone-launch threshold (its neighbours overlap it).
+static std::vector<size_t> pipeline_plan(const DeviceCtx& ctx, int format, const txp_params* p, size_t w, size_t rows, uint64_t* lane_chunks) {
     const size_t bw = (w + 3) / 4;
     size_t rows_per_chunk = pipeline_rows_per_chunk(format, p, w, rows);
     std::vector<size_t> plan;
+    *lane_chunks = 0;
     const bool cluster = format <= BC3 && p->algorithm != RANGE_FIT, forced = g_chunk_mib.load(std::memory_order_relaxed) != 0;
     const int growth = g_plan_growth.load(std::memory_order_relaxed);
+    const int wave_min = g_wave_plan.load(std::memory_order_relaxed);
+    if (const char* ex = getenv("TXP_PLAN")) {              // experiments only: "rows[xN],rows,...;L=<index of the first lane chunk>"
+        size_t sum = 0, first_lane = 64;
+        for (const char* q = ex; *q && *q != ';';) {
+            char* end;
+            const size_t r = strtoul(q, &end, 10);
+            size_t rep = 1;
+            if (*end == 'x') rep = strtoul(end + 1, &end, 10);
+            for (size_t i = 0; i < rep && r > 0; ++i) { plan.push_back(r); sum += r; }
+            q = (*end == ',') ? end + 1 : end;
+            if (end == q && *q && *q != ';') break;
+        }
+        if (const char* l = strstr(ex, "L=")) first_lane = strtoul(l + 2, nullptr, 10);
+        if (!plan.empty() && sum >= rows) {
+            for (size_t i = first_lane; i < plan.size() && i < 64; ++i) *lane_chunks |= 1ull << i;
+            return plan;
+        }
+        plan.clear();
+    }
+    if (cluster && !forced && wave_min > 0 && p->algorithm == CLUSTER_FIT && g_colour_variant.load(std::memory_order_relaxed) == 0) {
+        const uint64_t wave = lane_wave_blocks(ctx);
+        uint64_t k = (uint64_t)rows * bw / wave;
+        const size_t r1 = (size_t)(wave / bw), r2 = (size_t)(2 * wave / bw);        // block rows of a one-round / two-round chunk
+        const size_t min_rows = (16384 + bw - 1) / bw;                             // a launch of at least 16 Ki blocks
+        if (k >= (uint64_t)wave_min && k <= (uint64_t)g_wave_plan_max.load(std::memory_order_relaxed) && r1 >= min_rows) {
+            std::vector<size_t> lane;
+            size_t lane_rows = 0;
+            const uint64_t cw = (uint64_t)std::max(2, g_wave_chunk.load(std::memory_order_relaxed));
+            const size_t rc = (size_t)(cw * wave / bw);
+            for (; k > cw && cw > 2; k -= cw) { lane.push_back(rc); lane_rows += rc; }
+            for (; k > 2; k -= 2) { lane.push_back(r2); lane_rows += r2; }
+            for (; k > 0; --k) { lane.push_back(r1); lane_rows += r1; }
+            size_t head = rows - lane_rows;
+            if (head < min_rows) { head += lane.back(); lane.pop_back(); }           // (nearly) whole rounds: the last single round opens the pipeline instead
+            size_t first = head / 4 > min_rows ? head / 4 : min_rows;
+            if (head < first + min_rows) first = head;
+            plan.push_back(first);
+            if (head > first) plan.push_back(head - first);
+            for (const size_t r : lane) { *lane_chunks |= 1ull << plan.size(); plan.push_back(r); }
+            return plan;
+        }
+    }
     if (cluster && !forced && p->algorithm == ITERATIVE_CLUSTER_FIT && rows > rows_per_chunk && rows_per_chunk * 16 * w >= ITER_CHUNK_BYTES / 2) {
         const long long lm = g_lane_min_blocks.load(std::memory_order_relaxed);
         size_t first = ((size_t)(lm > 0 ? lm : 1) / 2 + bw - 1) / bw;
@@ -817,7 +871,8 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
     const size_t bpp = layout_bpp(layout);
     const size_t bs = (size_t)block_bytes(format), bw = (w + 3) / 4;
     const bool in_direct = dma_direct(rgba), out_direct = dma_direct(out);
-    const std::vector<size_t> plan = pipeline_plan(format, p, w, row1 - row0);
+    uint64_t lane_chunks = 0;
+    const std::vector<size_t> plan = pipeline_plan(c, format, p, w, row1 - row0, &lane_chunks);
     const size_t rows_per_chunk = plan.size() > 1 ? plan[1] : plan[0];
     int rc = TXP_OK;
     size_t chunk = 0;
@@ -858,7 +913,8 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
             }
         }
         const BlockSource bsrc = image_source(s.d_in, w, h_sub, nblk);
-        if ((rc = launch_encode(c, format, bsrc, p, s.d_out, s.stream, TXP_HOST_CONCURRENT != 0 && (row1 - row0) > 2 * rows_per_chunk)) != TXP_OK) break;
+        if ((rc = launch_encode(c, format, bsrc, p, s.d_out, s.stream,
+                                (chunk < 64 && ((lane_chunks >> chunk) & 1u)) || (TXP_HOST_CONCURRENT != 0 && (row1 - row0) > 2 * rows_per_chunk))) != TXP_OK) break;
         uint8_t* dst = out + (r - row0) * bw * bs;
         if (out_direct) {
             TXP_CUDA_BREAK(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDefault, s.stream));
@@ -1109,6 +1165,9 @@ const char* txp_version(void) { return "texpresso_b200 0.1 (sm_100a)"; }
 
 int txp_debug_set(int key, int value) {
     if (key == 0) { if (value < 0 || value > 4) return fail(TXP_ERR_ARGUMENT, "colour variant must be 0..4"); g_colour_variant.store(value); return TXP_OK; }
+    if (key == 7) { if (value < 2 || value > 16) return fail(TXP_ERR_ARGUMENT, "round-aligned plan: rounds per lane chunk, 2..16"); g_wave_chunk.store(value); return TXP_OK; }
+    if (key == 6) { if (value < 0 || value > 120) return fail(TXP_ERR_ARGUMENT, "round-aligned plan: largest shard in rounds, 0..120"); g_wave_plan_max.store(value); return TXP_OK; }
+    if (key == 5) { if (value < 0 || value > 64) return fail(TXP_ERR_ARGUMENT, "round-aligned plan: smallest shard in rounds, 0..64 (0 = off)"); g_wave_plan.store(value); return TXP_OK; }
     if (key == 4) { if (value < 0 || value > 16) return fail(TXP_ERR_ARGUMENT, "plan growth must be 0..16"); g_plan_growth.store(value); return TXP_OK; }
     if (key == 3) { if (value < 0 || value > 4096) return fail(TXP_ERR_ARGUMENT, "chunk override must be 0..4096 MiB"); g_chunk_mib.store(value); return TXP_OK; }
     if (key == 2) { if (value < 0 || value > 100) return fail(TXP_ERR_ARGUMENT, "hybrid tail threshold must be 0..100 (percent of a lane round)"); g_hybrid_tail.store(value); return TXP_OK; }
@@ -1126,6 +1185,8 @@ int txp_debug_get(int key, uint64_t* value) {
     case 4: *value = g_path_warp.load(); return TXP_OK;          // (Iterative)ClusterFit launches that took the warp-per-block search
     case 5: *value = g_path_hybrid.load(); return TXP_OK;        // ClusterFit launches split into full lane rounds + a warp-per-block tail
     case 6: *value = (uint64_t)g_hybrid_tail.load(); return TXP_OK;
+    case 7: *value = (uint64_t)g_wave_plan.load(); return TXP_OK;
+    case 8: *value = (uint64_t)g_wave_plan_max.load(); return TXP_OK;
     default: return fail(TXP_ERR_ARGUMENT, "unknown debug key");
     }
 }
