@@ -320,7 +320,7 @@ def test_fullsize_8192_bc1_iterative_auto_path_vs_oracle(T):
     lane0, warp0 = _debug_get(3), _debug_get(4)
     a = T.Format.Bc1.compress(img, w, h, tp)
     lane, warp = _debug_get(3) - lane0, _debug_get(4) - warp0
-    assert lane >= 3 and warp <= 1, (lane, warp)             # a 64-row first chunk (warp kernels), then three chunks of ~83 MiB
+    assert lane >= 2 and warp <= 1, (lane, warp)             # a 64-row first chunk (warp kernels), then two chunks of 124 MiB
     rowbytes = (w // 4) * 8
     for y0 in (0, 1024, 4096 + 512, h - 32):                  # first chunk, chunk interiors, last rows
         want = O.compress(0, img[y0:y0 + 32, :2048], 2048, 32, op, threads=8).reshape(8, -1)

@@ -746,8 +746,11 @@ static void slots_abandon(DeviceCtx& c) {
 //    64 MiB 19.50 ms end to end for BC3 ClusterFit 8192^2 against 18.42 ms device-resident -- the copies of the first and the
 //    last chunk are the exposed ones)
 //  * IterativeClusterFit: every launch ends in a drain tail of up to 8 orderings per block, twice for BC1, so few large launches:
-//    chunks of ~ITER_CHUNK_BYTES (same file: 48 MiB chunks 60.6 ms, 96 MiB 57.6 ms, 192 MiB 59.2 ms against 53.7 ms)
-constexpr size_t ITER_CHUNK_BYTES = 96u << 20;
+//    chunks of ~ITER_CHUNK_BYTES (same file: 48 MiB chunks 60.6 ms, 96 MiB 57.6 ms, 192 MiB 59.2 ms against 53.7 ms; the persistent
+//    search kernels of different chunks do not overlap -- a chunk's setup kernel finds no room on an SM full of search CTAs -- so every
+//    further chunk adds two drain tails, about 1 ms: profiles/plan_iter_r02.txt, 8192^2 BC1: 64 + 2 x 992 block rows 57.1 ms,
+//    64 + 3 x 662 rows 57.9 ms, 64 + 4 x 496 rows 59.4 ms, one chunk 59.7 ms, device-resident 54.3 ms)
+constexpr size_t ITER_CHUNK_BYTES = 128u << 20;
 static size_t pipeline_rows_per_chunk(int format, const txp_params* p, size_t w, size_t rows) {
     const size_t bw = (w + 3) / 4, row_bytes = 16 * w;
     size_t chunk_bytes = rows * row_bytes / 6;
