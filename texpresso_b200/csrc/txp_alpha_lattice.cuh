@@ -49,6 +49,9 @@ __device__ uint4 g_alpha_lattice[512];            // TXP_ALPHA_LATTICE (alpha_la
 #define TXP_LAT_MM 0       // min / max: 0 = VIMNMX3 trees, 1 = two-input VIMNMX
 #endif
 
+#ifndef TXP_LAT_SCALAR
+#define TXP_LAT_SCALAR 0   // slot arithmetic of the regular path: 0 = packed FADD2 + FFMA2 (two pixels each), 1 = scalar FADD + FFMA
+#endif
 #ifndef TXP_LAT_PACK
 #define TXP_LAT_PACK 0     // index bytes -> 48-bit field: 0 = shift / or / mask (ALU pipe), 1 = multiply-gather (IMAD with immediates, FMA pipe) + masks
 #endif
@@ -79,11 +82,21 @@ __device__ __forceinline__ int lattice_book(const uint32_t vm[16], const uint32_
     uint32_t cc = 0, cv = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        float t0, t1, t2, t3;
+#if TXP_LAT_SCALAR
+        // scalar FADD + FFMA per pixel: one dispatch slot each, and the ALU pipe keeps issuing next to them; a packed FADD2 / FFMA2 holds the
+        // dispatch port for two cycles and serialises with the ALU-pipe instructions around it (tools/micro/half2_rate.cu: FFMA2 / PRMT 1:1
+        // issues 1.6 warp-instructions per clock per SM, IMAD / PRMT 1:1 issues 3.9)
+        t0 = __fmaf_rn(__fsub_rn(__uint_as_float(vm[4 * k]), origin), a, MAGIC23);
+        t1 = __fmaf_rn(__fsub_rn(__uint_as_float(vm[4 * k + 1]), origin), a, MAGIC23);
+        t2 = __fmaf_rn(__fsub_rn(__uint_as_float(vm[4 * k + 2]), origin), a, MAGIC23);
+        t3 = __fmaf_rn(__fsub_rn(__uint_as_float(vm[4 * k + 3]), origin), a, MAGIC23);
+#else
         const f32x2 d01 = sub2(pk(__uint_as_float(vm[4 * k]), __uint_as_float(vm[4 * k + 1])), o2);
         const f32x2 d23 = sub2(pk(__uint_as_float(vm[4 * k + 2]), __uint_as_float(vm[4 * k + 3])), o2);
-        float t0, t1, t2, t3;
         upk(fma2(d01, a2, m2), t0, t1);
         upk(fma2(d23, a2, m2), t2, t3);
+#endif
         // low 16 bits: four slot nibbles (the magic's low 22 bits are zero, so nothing else reaches them)
         const uint32_t s = ((__float_as_uint(t3) * 16u + __float_as_uint(t2)) * 16u + __float_as_uint(t1)) * 16u + __float_as_uint(t0);
         sel[k] = s;
