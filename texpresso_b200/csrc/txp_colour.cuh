@@ -247,7 +247,8 @@ __device__ void cluster_pass(const SetInfo& s, const EncodeParams& prm, const fl
             ow = ow0;
             degenerate = ow0_degenerate;
             // rank of point `lane` = its position in the ordering (inverse permutation through shared memory)
-            if (lane < count) ws->keys[(ow >> (4 * lane)) & 15ull] = lane;
+            // (a degenerate ordering repeats entries, SURVEY Q7: several lanes would write one slot -- its ranks are never used, see best_degenerate)
+            if (lane < count && !degenerate) ws->keys[(ow >> (4 * lane)) & 15ull] = lane;
             __syncwarp();
             rank = lane < 16 ? ws->keys[lane] : 0;
             __syncwarp();
