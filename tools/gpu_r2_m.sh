@@ -18,6 +18,4 @@ cap ncu_lane_smooth_r02 cluster_lane_kernel 1 4194304 python tools/prof_lane.py 
 cap ncu_range_r02 range_encode 1 1048576 python tools/prof_range.py
 cap ncu_alpha_bc4_r02 alpha_lattice 1 131072 python tools/prof_alpha.py
 cap ncu_alpha_bc5_r02 alpha_lattice 4 131072 python tools/prof_alpha.py
-cp /tmp/ncu_alpha_bc5_r02.ncu-rep gpurun_out/ 2>/dev/null
-./tools/micro/alpha_ab r02m 0 2>&1 | tee gpurun_out/alpha_ab_r02m.txt
 du -sh gpurun_out; ls -la gpurun_out
