@@ -352,6 +352,25 @@ def test_lane_chunk_rows_round_up(T):
     assert np.array_equal(a[200 * 1500 * 8:208 * 1500 * 8], want)
 
 
+@pytest.mark.parametrize("fmt", range(5))
+def test_empty_and_one_pixel_images(T, fmt):
+    """height 0: compressed_size is 0 and the reference's loops run zero times (lib.rs:300-305, :128-134); 1 x 1: one block with 15 masked
+    pixels.  Every host entry point must agree with the oracle on both."""
+    tp, op = _params(T, 1, O.PERCEPTUAL)
+    F = T.Format(fmt)
+    empty = np.zeros(0, np.uint8)
+    assert F.compressed_size(16, 0) == 0
+    assert F.compress(empty, 16, 0, tp).size == 0
+    assert F.decompress(empty, 16, 0).size == 0
+    assert T.compress_multi(fmt, empty, 16, 0, tp, n_gpus=1).size == 0
+    px = np.array([[[200, 100, 50, 128]]], np.uint8)
+    got = F.compress(px, 1, 1, tp)
+    assert np.array_equal(got, O.compress(fmt, px, 1, 1, op))
+    assert np.array_equal(F.decompress(got, 1, 1), O.decompress(fmt, got, 1, 1))
+    outs = T.compress_batch(fmt, [(px, 1, 1), (empty, 8, 0), (px, 1, 1)], tp, n_gpus=1)
+    assert np.array_equal(outs[0], got) and outs[1].size == 0 and np.array_equal(outs[2], got)
+
+
 @pytest.mark.parametrize("fmt", [0, 2])
 def test_round_aligned_plan_shard_vs_oracle(T, fmt):
     """One rank's shard of the metric texture at 8 ranks (8192 x 1024 = 4.6 rounds of the lane-per-block search) through the host API:

@@ -67,7 +67,7 @@ def _ptr(a):
 def _out(output, name="output"):
     """A caller-supplied output must be written in place: contiguous uint8, no temporary copy."""
     out = _u8(output, name)
-    if not np.shares_memory(out, output):
+    if out.size and not np.shares_memory(out, output):           # (an empty array shares no memory with anything)
         raise ValueError(f"{name} must be a contiguous uint8 array")
     return out
 
