@@ -198,18 +198,33 @@ __device__ __forceinline__ uint2 range_colour_rolled(uint32_t px[16], const uint
     // ---- range.rs:67-86: first point starts both ends; strict < / else-if > over the following points ----------
     int is = 0, ie = 0;
     float mn = 0.f, mx = 0.f;
-    bool found = false;
+    if (__all_sync(__activemask(), active16 == 0xFFFFu)) {           // warp-uniform: a warp with both kinds of block would pay for both loops
+        // Every pixel carries a colour (the usual case), so pixel 0 is the first point.  A pixel that is not a point repeats the colour of an
+        // earlier point, hence its projection bit for bit, and the strict comparisons ignore it: no is-a-point test per pixel.  mn <= mx always,
+        // so "d < mn" and "d > mx" exclude each other and the reference's else-if needs no spelling out.  (NaN projections compare false throughout.)
+        const float4 p0 = col[0];
+        mn = mx = add(add(mul(p0.x, axis.x), mul(p0.y, axis.y)), mul(p0.z, axis.z));
+#pragma unroll 5
+        for (int i = 1; i < 16; ++i) {
+            const float4 p = col[i * ROLL_THREADS];
+            const float d = add(add(mul(p.x, axis.x), mul(p.y, axis.y)), mul(p.z, axis.z));
+            if (d < mn) { is = i; mn = d; }
+            if (d > mx) { ie = i; mx = d; }
+        }
+    } else {
+        bool found = false;
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const float4 p = col[i * ROLL_THREADS];
-        const bool is_new = p.w > 0.0f;                  // weights of points are sqrt of positive totals
-        const float d = add(add(mul(p.x, axis.x), mul(p.y, axis.y)), mul(p.z, axis.z));
-        const bool first = is_new && !found;
-        const bool lower = is_new && found && d < mn;
-        const bool upper = is_new && found && !(d < mn) && d > mx;
-        if (first || lower) { is = i; mn = d; }
-        if (first || upper) { ie = i; mx = d; }
-        found = found || is_new;
+        for (int i = 0; i < 16; ++i) {
+            const float4 p = col[i * ROLL_THREADS];
+            const bool is_new = p.w > 0.0f;              // weights of points are sqrt of positive totals
+            const float d = add(add(mul(p.x, axis.x), mul(p.y, axis.y)), mul(p.z, axis.z));
+            const bool first = is_new && !found;
+            const bool lower = is_new && found && d < mn;
+            const bool upper = is_new && found && !(d < mn) && d > mx;
+            if (first || lower) { is = i; mn = d; }
+            if (first || upper) { ie = i; mx = d; }
+            found = found || is_new;
+        }
     }
     // clamp to [0,1] is the identity on c/255; snap to the 5:6:5 grid (range.rs:88-98)
     const float4 ps = col[is * ROLL_THREADS], pe = col[ie * ROLL_THREADS];
