@@ -290,7 +290,7 @@ static std::atomic<int> g_chunk_mib{[] { const char* v = getenv("TXP_CHUNK_MIB")
 static std::atomic<int> g_plan_growth{[] { const char* v = getenv("TXP_PLAN_GROWTH"); return v ? atoi(v) : 3; }()};   // geometric chunk plan of small ClusterFit shards; <= 1: off
 // round-aligned chunk plan of small ClusterFit shards (pipeline_plan): smallest shard, in rounds of the lane-per-block search, that takes it; 0 = off
 static std::atomic<int> g_wave_plan{[] { const char* v = getenv("TXP_WAVE_PLAN"); return v ? atoi(v) : 4; }()};
-static std::atomic<int> g_wave_plan_max{[] { const char* v = getenv("TXP_WAVE_PLAN_MAX"); return v ? atoi(v) : 20; }()};   // ... and the largest (<= 120 rounds: 64 chunks)
+static std::atomic<int> g_wave_plan_max{[] { const char* v = getenv("TXP_WAVE_PLAN_MAX"); return v ? atoi(v) : 40; }()};   // ... and the largest (<= 120 rounds: 64 chunks)
 static std::atomic<int> g_wave_chunk{[] { const char* v = getenv("TXP_WAVE_CHUNK"); return v ? atoi(v) : 2; }()};   // rounds per lane chunk of that plan
 static std::atomic<int> g_hybrid_tail{[] { const char* v = getenv("TXP_HYBRID_TAIL"); return v ? atoi(v) : TXP_TAIL_FRAC; }()};
 constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (292 B of scratch per block)
@@ -802,7 +802,7 @@ static std::vector<size_t> pipeline_plan(const DeviceCtx& ctx, int format, const
             const size_t r = strtoul(q, &end, 10);
             size_t rep = 1;
             if (*end == 'x') rep = strtoul(end + 1, &end, 10);
-            for (size_t i = 0; i < rep && r > 0; ++i) { plan.push_back(r); sum += r; }
+            for (size_t i = 0; i < rep && r > 0 && plan.size() < 4096; ++i) { plan.push_back(r); sum += r; }
             q = (*end == ',') ? end + 1 : end;
             if (end == q && *q && *q != ';') break;
         }

@@ -30,7 +30,7 @@ for rows in (512, 1024, 2048):
                     F.compress(hin.numpy(), w, h, prm, output=outs[k].numpy())
                     if i >= 2:
                         ts[k].append(1e3 * (time.perf_counter() - t0))
-            L.txp_debug_set(6, 20); L.txp_debug_set(7, 2)
+            L.txp_debug_set(6, 40); L.txp_debug_set(7, 2)
             rec = {"rows": rows, "fmt": "bc1" if fmt == 0 else "bc3", "input": kind, "same": all(bool(torch.equal(outs[KNOBS[0]], outs[k])) for k in KNOBS)}
             for k in KNOBS:
                 rec[f"ms_max{k[0]}_c{k[1]}"] = round(sorted(ts[k])[len(ts[k]) // 2], 3)
