@@ -5,14 +5,13 @@ import json, os, sys, time, pathlib, subprocess, ctypes
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 PLANS = {
     "auto": "",
-    "one_chunk": "2048;L=0",
-    "64_1984": "64,1984;L=1",
     "64_992x2": "64,992x2;L=1",
-    "64_661x3": "64,662x3;L=1",
-    "64_496x4": "64,496x4;L=1",
-    "32_96_640x3": "32,96,640x3;L=2",
-    "64_256_576x3": "64,256,576x3;L=1",
-    "128_640x3": "128,640x3;L=0",
+    "128_1920": "128,1920;L=1",
+    "192_1856": "192,1856;L=1",
+    "256_1792": "256,1792;L=1",
+    "256_1792_lane": "256,1792;L=0",
+    "384_1664_lane": "384,1664;L=0",
+    "32_224_1792": "32,224,1792;L=2",
 }
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     sys.path.insert(0, str(ROOT))
