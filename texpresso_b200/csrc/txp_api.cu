@@ -6,6 +6,8 @@
 // every data path ends in a kernel launch or an error code.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -296,6 +298,74 @@ static std::atomic<int> g_hybrid_tail{[] { const char* v = getenv("TXP_HYBRID_TA
 constexpr uint64_t LANE_CHUNK_BLOCKS = 4u << 20;    // blocks per setup/search launch pair of the lane path (292 B of scratch per block)
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
+
+// ---- staging copies of pageable caller buffers ---------------------------------------------------------------------------------------
+// A caller who hands over ordinary (pageable) memory -- the reference's &[u8] slices (lib.rs:287-294) -- gets every pipeline chunk copied through
+// pinned staging buffers.  One thread moves ~11 GB/s, a fifth of what the PCIe link takes, which made such calls 2-9x slower than calls on pinned
+// buffers (profiles/pageable_r02.jsonl: BC4 8192^2 23.3 ms against 5.0 ms).  A few helper threads split every large copy.  TXP_COPY_THREADS = threads
+// per copy including the caller (default 4, capped at half the hardware threads; <= 1: plain memcpy).  The pool is created on first use and never
+// joined (helpers sleep on a condition variable; a static destructor racing with the CUDA runtime's own teardown would be worse than the leak).
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }
+    void copy(void* dst, const void* src, size_t n) {
+        constexpr size_t MIN_PART = 512u << 10;
+        const size_t parts = std::min<size_t>((size_t)threads_, n / MIN_PART);
+        if (parts <= 1) { std::memcpy(dst, src, n); return; }
+        const size_t step = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
+        std::atomic<int> left{0};
+        uint8_t* d = static_cast<uint8_t*>(dst);
+        const uint8_t* s = static_cast<const uint8_t*>(src);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t off = step; off < n; off += step) { queue_.push_back({d + off, s + off, std::min(step, n - off), &left}); left.fetch_add(1, std::memory_order_relaxed); }
+        }
+        cv_.notify_all();
+        std::memcpy(d, s, std::min(step, n));
+        // help with the queue (possibly another caller's parts) until this copy's parts are done, then wait for the ones in flight
+        for (;;) {
+            Part p;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (left.load(std::memory_order_acquire) == 0 || queue_.empty()) break;
+                p = queue_.front(); queue_.pop_front();
+            }
+            run(p);
+        }
+        std::unique_lock<std::mutex> lk(done_mu_);
+        done_cv_.wait(lk, [&] { return left.load(std::memory_order_acquire) == 0; });
+    }
+private:
+    struct Part { uint8_t* dst; const uint8_t* src; size_t n; std::atomic<int>* left; };
+    CopyPool() {
+        const char* v = getenv("TXP_COPY_THREADS");
+        int want = v ? atoi(v) : 4;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && want > hw / 2) want = hw / 2;
+        threads_ = want < 1 ? 1 : want;
+        for (int i = 1; i < threads_; ++i) std::thread([this] { worker(); }).detach();
+    }
+    void run(const Part& p) {
+        std::memcpy(p.dst, p.src, p.n);
+        if (p.left->fetch_sub(1, std::memory_order_acq_rel) == 1) { std::lock_guard<std::mutex> lk(done_mu_); done_cv_.notify_all(); }
+    }
+    void worker() {
+        for (;;) {
+            Part p;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return !queue_.empty(); });
+                p = queue_.front(); queue_.pop_front();
+            }
+            run(p);
+        }
+    }
+    int threads_ = 1;
+    std::mutex mu_, done_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::deque<Part> queue_;
+};
+static inline void host_copy(void* dst, const void* src, size_t n) { CopyPool::get().copy(dst, src, n); }
 
 #define TXP_CUDA(expr)                                                                          \
     do {                                                                                        \
@@ -715,8 +785,8 @@ static int check_dims(size_t w, size_t h) {
 static int slot_wait(Slot& s) {
     if (!s.busy) return TXP_OK;
     TXP_CUDA(cudaEventSynchronize(s.done));
-    if (s.user_out) { std::memcpy(s.user_out, s.h_out, s.user_out_bytes); s.user_out = nullptr; }
-    for (const Slot::Deferred& d : s.deferred) std::memcpy(d.dst, s.h_out + d.off, d.n);
+    if (s.user_out) { host_copy(s.user_out, s.h_out, s.user_out_bytes); s.user_out = nullptr; }
+    for (const Slot::Deferred& d : s.deferred) host_copy(d.dst, s.h_out + d.off, d.n);
     s.deferred.clear();
     s.busy = false;
     return TXP_OK;
@@ -899,7 +969,7 @@ static int compress_host_rows(DeviceCtx& c, int format, const uint8_t* rgba, siz
             const uint8_t* src_ptr = rgba + y0 * w * bpp;
             if (!in_direct) {
                 if ((rc = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) break;
-                std::memcpy(s.h_in, src_ptr, in_bytes);
+                host_copy(s.h_in, src_ptr, in_bytes);
                 src_ptr = s.h_in;
             }
             TXP_CUDA_BREAK(cudaMemcpyAsync(bpp == 4 ? s.d_in : s.d_raw, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
@@ -961,7 +1031,7 @@ static int decompress_host_rows(DeviceCtx& c, int format, const uint8_t* data, s
         const uint8_t* src_ptr = data + (r - row0) * bw * bs;
         if (!in_direct) {
             if ((rc = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) break;
-            std::memcpy(s.h_in, src_ptr, in_bytes);
+            host_copy(s.h_in, src_ptr, in_bytes);
             src_ptr = s.h_in;
         }
         TXP_CUDA_BREAK(cudaMemcpyAsync(s.d_in, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
@@ -1057,7 +1127,7 @@ static int group_enqueue_impl(DeviceCtx& ctx, Slot& s, int format, const uint8_t
         if (!dma_direct(src_ptr)) {
             if (!staged_in && (rc = grow_pinned(&s.h_in, &s.h_in_cap, (size_t)k * in_bytes)) != TXP_OK) return rc;
             staged_in = true;
-            std::memcpy(s.h_in + (size_t)t * in_bytes, src_ptr, in_bytes);
+            host_copy(s.h_in + (size_t)t * in_bytes, src_ptr, in_bytes);
             src_ptr = s.h_in + (size_t)t * in_bytes;
         }
         TXP_CUDA(cudaMemcpyAsync(s.d_in + (size_t)t * tex_px * 4, src_ptr, in_bytes, cudaMemcpyDefault, s.stream));
@@ -1648,7 +1718,7 @@ int txp_decompress_batch(int format, const uint8_t* const* data, const size_t* w
                         const uint8_t* src_ptr = data[t];
                         if (!dma_direct(src_ptr)) {
                             if ((r = grow_pinned(&s.h_in, &s.h_in_cap, in_bytes)) != TXP_OK) break;
-                            std::memcpy(s.h_in, src_ptr, in_bytes);
+                            host_copy(s.h_in, src_ptr, in_bytes);
                             src_ptr = s.h_in;
                         }
                         int rc = TXP_OK;
