@@ -303,7 +303,7 @@ static int fail(int code, const std::string& msg) { t_last_error = msg; return c
 // A caller who hands over ordinary (pageable) memory -- the reference's &[u8] slices (lib.rs:287-294) -- gets every pipeline chunk copied through
 // pinned staging buffers.  One thread moves ~11 GB/s, a fifth of what the PCIe link takes, which made such calls 2-9x slower than calls on pinned
 // buffers (profiles/pageable_r02.jsonl: BC4 8192^2 23.3 ms against 5.0 ms).  A few helper threads split every large copy.  TXP_COPY_THREADS = threads
-// per copy including the caller (default 4, capped at half the hardware threads; <= 1: plain memcpy).  The pool is created on first use and never
+// per copy including the caller (default 8, capped at half the hardware threads; <= 1: plain memcpy).  The pool is created on first use and never
 // joined (helpers sleep on a condition variable; a static destructor racing with the CUDA runtime's own teardown would be worse than the leak).
 class CopyPool {
 public:
@@ -339,7 +339,7 @@ private:
     struct Part { uint8_t* dst; const uint8_t* src; size_t n; std::atomic<int>* left; };
     CopyPool() {
         const char* v = getenv("TXP_COPY_THREADS");
-        int want = v ? atoi(v) : 4;
+        int want = v ? atoi(v) : 8;
         const int hw = (int)std::thread::hardware_concurrency();
         if (hw > 0 && want > hw / 2) want = hw / 2;
         threads_ = want < 1 ? 1 : want;
