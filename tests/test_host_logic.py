@@ -130,3 +130,25 @@ def test_debug_knobs_reject_bad_values():
     assert L.txp_debug_set(1, -5) != 0
     assert L.txp_debug_set(1, 0) != 0
     assert L.txp_debug_set(0, 7) != 0
+
+
+def test_copy_pool_matches_memcpy():
+    """The multi-threaded staging copy used for pageable caller buffers (CopyPool): every size class (below the split threshold, odd sizes,
+    unaligned ends, many parts) and several host threads copying at once give plain-memcpy results.  Host-only code: runs without a GPU."""
+    import ctypes, threading
+    from texpresso_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 4095, (512 << 10) - 1, 1 << 20, (1 << 20) + 1, (5 << 20) + 3, (24 << 20) + 4097):
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        dst = np.zeros(n + 64, np.uint8)
+        assert L.txp_debug_host_copy(ctypes.c_void_p(dst.ctypes.data + 7), ctypes.c_void_p(src.ctypes.data), n) == 0
+        assert np.array_equal(dst[7:7 + n], src) and not dst[:7].any() and not dst[7 + n:].any()
+    srcs = [rng.integers(0, 256, (3 << 20) + 11 * i, dtype=np.uint8) for i in range(8)]
+    dsts = [np.zeros(s.size, np.uint8) for s in srcs]
+    def work(i):
+        for _ in range(6):
+            L.txp_debug_host_copy(ctypes.c_void_p(dsts[i].ctypes.data), ctypes.c_void_p(srcs[i].ctypes.data), srcs[i].size)
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert all(np.array_equal(a, b) for a, b in zip(srcs, dsts))

@@ -1264,6 +1264,12 @@ int txp_debug_get(int key, uint64_t* value) {
     }
 }
 
+int txp_debug_host_copy(void* dst, const void* src, size_t n) {
+    if (n && (!dst || !src)) return fail(TXP_ERR_ARGUMENT, "null pointer");
+    host_copy(dst, src, n);
+    return TXP_OK;
+}
+
 int txp_measure_fp32_issue(double* lane_ops_per_second) {
     if (!lane_ops_per_second) return fail(TXP_ERR_ARGUMENT, "null pointer");
     DeviceCtx* c;
