@@ -16,6 +16,9 @@
 #include <thread>
 #include <vector>
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 #include <cuda.h>                 // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved at run time through cudaGetDriverEntryPoint; libcuda is not linked)
 
 #include "../../include/texpresso_b200.h"
@@ -305,13 +308,37 @@ static int fail(int code, const std::string& msg) { t_last_error = msg; return c
 // buffers (profiles/pageable_r02.jsonl: BC4 8192^2 23.3 ms against 5.0 ms).  A few helper threads split every large copy.  TXP_COPY_THREADS = threads
 // per copy including the caller (default 8, capped at half the hardware threads; <= 1: plain memcpy).  The pool is created on first use and never
 // joined (helpers sleep on a condition variable; a static destructor racing with the CUDA runtime's own teardown would be worse than the leak).
+// One part of a staging copy.  Large parts use non-temporal stores (SSE2 MOVNTDQ): the destination is either a pinned buffer the DMA engine reads
+// next or a caller buffer nobody reads soon, so write-allocating it in the cache only adds a read of every destination line (TXP_COPY_NT=0: memcpy).
+static void copy_part(uint8_t* d, const uint8_t* s, size_t n) {
+#if defined(__x86_64__) || defined(_M_X64)
+    static const bool nt = [] { const char* v = getenv("TXP_COPY_NT"); return !v || atoi(v) != 0; }();
+    if (nt && n >= (256u << 10)) {
+        const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+        std::memcpy(d, s, head);
+        d += head; s += head; n -= head;
+        const size_t lines = n / 64;
+        for (size_t i = 0; i < lines; ++i, d += 64, s += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d), a); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+        }
+        _mm_sfence();
+        std::memcpy(d, s, n - lines * 64);
+        return;
+    }
+#endif
+    std::memcpy(d, s, n);
+}
+
 class CopyPool {
 public:
     static CopyPool& get() { static CopyPool* p = new CopyPool(); return *p; }
     void copy(void* dst, const void* src, size_t n) {
         constexpr size_t MIN_PART = 512u << 10;
         const size_t parts = std::min<size_t>((size_t)threads_, n / MIN_PART);
-        if (parts <= 1) { std::memcpy(dst, src, n); return; }
+        if (parts <= 1) { copy_part(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), n); return; }
         const size_t step = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
         std::atomic<int> left{0};
         uint8_t* d = static_cast<uint8_t*>(dst);
@@ -321,7 +348,7 @@ public:
             for (size_t off = step; off < n; off += step) { queue_.push_back({d + off, s + off, std::min(step, n - off), &left}); left.fetch_add(1, std::memory_order_relaxed); }
         }
         cv_.notify_all();
-        std::memcpy(d, s, std::min(step, n));
+        copy_part(d, s, std::min(step, n));
         // help with the queue (possibly another caller's parts) until this copy's parts are done, then wait for the ones in flight
         for (;;) {
             Part p;
@@ -346,7 +373,7 @@ private:
         for (int i = 1; i < threads_; ++i) std::thread([this] { worker(); }).detach();
     }
     void run(const Part& p) {
-        std::memcpy(p.dst, p.src, p.n);
+        copy_part(p.dst, p.src, p.n);
         if (p.left->fetch_sub(1, std::memory_order_acq_rel) == 1) { std::lock_guard<std::mutex> lk(done_mu_); done_cv_.notify_all(); }
     }
     void worker() {
