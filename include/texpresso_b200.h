@@ -152,6 +152,7 @@ TXP_API int txp_debug_get(int key, uint64_t* value);   /* key 0 / 1: the knobs a
  * device, in lane-operations per second -- the measured counterpart of SMs x 128 lanes x clock, the roof of the ClusterFit
  * search under the reference's no-FMA-contraction contract. */
 TXP_API int txp_measure_fp32_issue(double* lane_ops_per_second);
+TXP_API int txp_debug_plan(int format, const txp_params* params, size_t width, size_t rows, int sm_count, size_t* chunk_rows, size_t max_chunks, size_t* n_chunks, uint64_t* lane_chunks);   /* the host pipeline's chunk plan for `rows` block rows of a `width`-pixel-wide image on a device with sm_count SMs: block rows per chunk in order, and a bit mask of the chunks that take the lane-per-block search below the lone-launch threshold; host-only, testable without a GPU */
 TXP_API int txp_debug_host_copy(void* dst, const void* src, size_t n);   /* the multi-threaded staging copy the library uses for pageable caller buffers (CopyPool, TXP_COPY_THREADS), exposed so that it can be tested without a GPU */
 TXP_API int txp_debug_set(int key, int value);   /* tuning knobs for A/B measurements; key 0: ClusterFit kernel structure 0 auto, 1 fused, 2 warp per block, 3 lane per block; key 1: smallest launch (blocks) that takes the lane-per-block search in auto mode; key 0 value 4: full lane rounds + warp-per-block tail; key 2: tail threshold of that split in percent of a round (0 = off, default); key 3: host pipeline chunk size override in MiB (0 = automatic); key 4: growth factor of the geometric chunk plan of small ClusterFit shards; key 5: smallest shard, in rounds of the lane-per-block search, that takes the round-aligned chunk plan (0 = off, default 4); key 6: the largest such shard in rounds (default 40); key 7: rounds per lane chunk of that plan (default 2) */
 

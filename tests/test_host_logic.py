@@ -152,3 +152,53 @@ def test_copy_pool_matches_memcpy():
     ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
     [t.start() for t in ts]; [t.join() for t in ts]
     assert all(np.array_equal(a, b) for a, b in zip(srcs, dsts))
+
+
+def _plan(fmt, alg, w, rows, sms=148):
+    import texpresso_b200 as T
+    from texpresso_b200 import _lib
+    L = _lib.load()
+    p = T.Params(T.Algorithm(alg))._c()
+    out = (ctypes.c_size_t * 4096)()
+    n = ctypes.c_size_t(0)
+    lane = ctypes.c_uint64(0)
+    _lib.check(L.txp_debug_plan(fmt, ctypes.byref(p), w, rows, sms, out, 4096, ctypes.byref(n), ctypes.byref(lane)))
+    return list(out[:n.value]), lane.value
+
+
+def test_pipeline_chunk_plans():
+    """The host pipeline's chunk plan (pipeline_plan, host-only): the round-aligned plans of the metric texture and its shards on a 148-SM device,
+    and the invariants every plan must keep for any width / height / algorithm (the chunks cover the rows exactly, none is empty, lane chunks of
+    the round-aligned plan never exceed whole rounds of 148 x 6 x 128 lanes and come after the small warp-per-block head)."""
+    wave = 148 * 6 * 128
+    # one rank of eight: 256 block rows of the 8192-wide texture = 4.61 rounds -> 0.61 round first (8 + 27 rows), then 2 + 1 + 1 rounds
+    assert _plan(2, 1, 8192, 256) == ([8, 27, 111, 55, 55], 0b11100)
+    assert _plan(0, 1, 8192, 256) == ([8, 27, 111, 55, 55], 0b11100)
+    rows, lane = _plan(2, 1, 8192, 512)                       # one rank of four: 9.2 rounds
+    assert rows == [13, 111, 111, 111, 111, 55] and lane == 0b111110
+    rows, lane = _plan(2, 1, 8192, 2048)                      # the whole texture: 36.9 rounds
+    assert sum(rows) == 2048 and rows[2:-2] == [111] * 17 and rows[-2:] == [55, 55] and lane == ((1 << len(rows)) - 1) & ~0b11
+    # below 4 rounds, above 40 rounds, RangeFit, IterativeClusterFit, BC4: the uniform plans, no forced lane chunks
+    for fmt, alg, w, r in ((2, 1, 8192, 192), (2, 1, 16384, 4096), (2, 0, 8192, 2048), (0, 2, 8192, 2048), (3, 1, 16384, 4096)):
+        rows, lane = _plan(fmt, alg, w, r)
+        assert sum(rows) == r and lane == 0 and min(rows) >= 1, (fmt, alg, w, r, rows)
+    assert _plan(0, 2, 8192, 2048)[0] == [64, 992, 992]       # IterativeClusterFit: half a lane launch, then two chunks of 124 MiB
+    assert _plan(2, 1, 8192, 0) == ([], 0)
+    rng = np.random.default_rng(11)
+    for _ in range(3000):
+        fmt, alg = int(rng.integers(0, 5)), int(rng.integers(0, 3))
+        w = int(rng.choice([1, 3, 4, 64, 100, 1000, 2048, 4096, 6000, 8192, 16384, 30000, 500000]))
+        r = int(rng.integers(0, 5000)) if w >= 1000 else int(rng.integers(0, 200000))
+        sms = int(rng.choice([148, 132, 20, 1]))
+        rows, lane = _plan(fmt, alg, w, r, sms)
+        bw = (w + 3) // 4
+        assert sum(rows) == r and all(x >= 1 for x in rows), (fmt, alg, w, r, sms, rows[:8])
+        if lane:
+            wv = sms * 6 * 128
+            first_lane = min(i for i in range(len(rows)) if (lane >> i) & 1)
+            assert fmt <= 2 and alg == 1 and 1 <= first_lane <= 2
+            assert all((lane >> i) & 1 for i in range(first_lane, len(rows)))
+            for i in range(first_lane, len(rows)):
+                k = max(1, round(rows[i] * bw / wv))
+                assert rows[i] * bw <= k * wv and rows[i] * bw >= 32768, (w, r, sms, rows, i)
+            assert sum(rows[:first_lane]) * bw < 2 * wv + 16384 + 2 * bw

@@ -13,7 +13,7 @@ EXPORTS = [
     "txp_compress_block_masked", "txp_decompress_block", "txp_compress_blocks", "txp_decompress_blocks",
     "txp_compress_device", "txp_decompress_device", "txp_shard_rows", "txp_compress_multi", "txp_compress_batch", "txp_decompress_multi", "txp_decompress_batch",
     "txp_mip_levels", "txp_mipchain_compressed_size", "txp_compress_mipchain", "txp_compress_batch_mips",
-    "txp_device_count", "txp_set_device", "txp_last_error", "txp_kernel_launches", "txp_version", "txp_debug_set", "txp_debug_get", "txp_measure_fp32_issue", "txp_debug_host_copy",
+    "txp_device_count", "txp_set_device", "txp_last_error", "txp_kernel_launches", "txp_version", "txp_debug_set", "txp_debug_get", "txp_measure_fp32_issue", "txp_debug_host_copy", "txp_debug_plan",
 ]
 
 
@@ -71,6 +71,7 @@ def load():
         "txp_debug_get": (ci, [ci, ctypes.POINTER(ctypes.c_uint64)]),
         "txp_measure_fp32_issue": (ci, [ctypes.POINTER(ctypes.c_double)]),
         "txp_debug_host_copy": (ci, [vp, vp, sz]),
+        "txp_debug_plan": (ci, [ci, pp, sz, sz, ci, ctypes.POINTER(sz), sz, ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_uint64)]),
     }
     for name in EXPORTS:
         fn = getattr(L, name)          # AttributeError if the library does not export it

@@ -1291,6 +1291,27 @@ int txp_debug_get(int key, uint64_t* value) {
     }
 }
 
+int txp_debug_plan(int format, const txp_params* params, size_t width, size_t rows, int sm_count, size_t* chunk_rows, size_t max_chunks, size_t* n_chunks,
+                   uint64_t* lane_chunks) {
+    int rc;
+    if ((rc = check_params(format, params)) != TXP_OK) return rc;
+    if (!chunk_rows || !n_chunks || !lane_chunks || width == 0 || sm_count < 1) return fail(TXP_ERR_ARGUMENT, "bad argument");
+    static DeviceCtx fake;                                // only sm_count is read by pipeline_plan
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    fake.sm_count = sm_count;
+    const std::vector<size_t> plan = pipeline_plan(fake, format, params, width, rows, lane_chunks);
+    size_t n = 0, chunk = 0;
+    for (size_t r = 0; r < rows; ++chunk) {               // the walk of compress_host_rows: the last entry repeats
+        const size_t step = std::max<size_t>(1, plan[chunk < plan.size() ? chunk : plan.size() - 1]);
+        if (n >= max_chunks) return fail(TXP_ERR_BUFFER_TOO_SMALL, "more chunks than max_chunks");
+        chunk_rows[n++] = std::min(step, rows - r);
+        r += step;
+    }
+    *n_chunks = n;
+    return TXP_OK;
+}
+
 int txp_debug_host_copy(void* dst, const void* src, size_t n) {
     if (n && (!dst || !src)) return fail(TXP_ERR_ARGUMENT, "null pointer");
     host_copy(dst, src, n);
