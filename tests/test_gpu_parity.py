@@ -479,3 +479,30 @@ def test_mip_chain_kernel_levels(T, w, h):
     got = T.compress_mipchain(0, img, w, h, tp)
     want = np.concatenate([O.compress(0, lv, lv.shape[1], lv.shape[0], op, threads=8) for lv in T.generate_mips(img, w, h)])
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("fmt,alg", [(0, 1), (2, 0), (4, 1), (1, 2)])
+def test_device_tensor_entry_points(T, fmt, alg):
+    """compress_device / decompress_device (torch CUDA tensors, asynchronous on torch's stream) give the bytes of the host calls; wrong
+    tensors are rejected before anything is launched."""
+    import torch
+    from texpresso_b200 import synth
+    w, h = 260, 134
+    img = synth.generate("smooth", w, h, seed=5)
+    tp, op = _params(T, alg, O.PERCEPTUAL)
+    d_in = torch.from_numpy(img.reshape(-1)).cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    d_out = T.compress_device(fmt, d_in, w, h, tp, stream=side)
+    d_dec = T.decompress_device(fmt, d_out, w, h, stream=side)
+    side.synchronize()
+    want = O.compress(fmt, img, w, h, op)
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    assert np.array_equal(d_dec.cpu().numpy(), O.decompress(fmt, want, w, h))
+    assert np.array_equal(T.compress_device(fmt, d_in, w, h, tp).cpu().numpy(), want)          # torch's current stream
+    with pytest.raises(TypeError):
+        T.compress_device(fmt, torch.from_numpy(img.reshape(-1)), w, h, tp)                      # host tensor
+    with pytest.raises(ValueError):
+        T.compress_device(fmt, d_in[:100], w, h, tp)                                             # too short
+    with pytest.raises(ValueError):
+        T.compress_device(fmt, d_in, w, h, tp, output=torch.empty(8, dtype=torch.uint8, device="cuda"))

@@ -185,6 +185,48 @@ def expand_pixels(pixels, width, height, layout=None):
     return out
 
 
+def _cuda_u8(t, name, need):
+    """A torch CUDA tensor as (pointer, bytes): uint8, contiguous, at least `need` bytes.  (torch is plumbing for device memory only.)"""
+    import torch
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.uint8 or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous uint8 CUDA tensor")
+    if t.numel() < need:
+        raise ValueError(f"{name}: {t.numel()} bytes, {need} needed")
+    return ctypes.c_void_p(t.data_ptr()), t.numel()
+
+
+def compress_device(fmt, rgba, width, height, params=None, output=None, stream=None):
+    """txp_compress_device: Format::compress (lib.rs:287-335) for callers whose RGBA8 image already lives in HBM.  rgba / output are torch
+    uint8 CUDA tensors on the current device; the kernels are enqueued on `stream` (a torch stream; default: torch's current stream) and the
+    call returns without waiting -- synchronise the stream before reading `output` on the host."""
+    import torch
+    F = Format(fmt)
+    params = params or Params()
+    need = F.compressed_size(width, height)
+    if output is None:
+        output = torch.empty(need, dtype=torch.uint8, device=rgba.device)
+    src, _ = _cuda_u8(rgba, "rgba", int(width) * int(height) * 4)
+    dst, out_len = _cuda_u8(output, "output", need)
+    st = (stream or torch.cuda.current_stream(rgba.device)).cuda_stream
+    cp = params._c()
+    check(load().txp_compress_device(int(F), src, width, height, ctypes.byref(cp), dst, out_len, ctypes.c_void_p(st)))
+    return output
+
+
+def decompress_device(fmt, data, width, height, output=None, stream=None):
+    """txp_decompress_device: Format::decompress (lib.rs:124-156) on torch uint8 CUDA tensors; asynchronous like compress_device."""
+    import torch
+    F = Format(fmt)
+    need = int(width) * int(height) * 4
+    if output is None:
+        output = torch.empty(need, dtype=torch.uint8, device=data.device)
+    src, _ = _cuda_u8(data, "data", F.compressed_size(width, height))
+    dst, out_len = _cuda_u8(output, "output", need)
+    st = (stream or torch.cuda.current_stream(data.device)).cuda_stream
+    check(load().txp_decompress_device(int(F), src, width, height, dst, out_len, ctypes.c_void_p(st)))
+    return output
+
+
 def shard_rows(height, rank, world):
     """Block-row range [begin, end) owned by `rank` of `world` (reference grain: one block row, lib.rs:300-305)."""
     a, b = ctypes.c_size_t(), ctypes.c_size_t()
