@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(ROLL_THREADS, TXP_SETUP_MIN_CTAS) cluster_setu
 // thread and round) and also leaves the window's permutation sorted by (points, punch-through), blocks that need no
 // search last: perm[s] = chunk-local block number of the s-th record in sorted order.  The 32 lanes of a search warp take
 // 32 consecutive entries of perm, i.e. (mostly) blocks whose loop nests have the same shape.
-constexpr int SETUP_WINDOW_ROUNDS = 8;
+#ifndef TXP_SETUP_WINDOW_ROUNDS
+#define TXP_SETUP_WINDOW_ROUNDS 8    // blocks per window = 128 x rounds (A/B: larger windows group the blocks better but leave the setup kernel fewer CTAs)
+#endif
+constexpr int SETUP_WINDOW_ROUNDS = TXP_SETUP_WINDOW_ROUNDS;
 constexpr int SETUP_WINDOW = ROLL_THREADS * SETUP_WINDOW_ROUNDS;
 
 template <int FMT>
