@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Randomised sweep of the public entry points against the oracle (beyond the fixed cases of tests/): random sizes, formats,
+"""Test infrastructure (it calls the oracle, so it lives under tests/): randomised sweep of the public entry points against the oracle (beyond the fixed cases): random sizes, formats,
 algorithms, weights, alpha weighting, over-long outputs, batches, mip chains, compact pixel layouts, multi-call decode.  Prints a summary."""
 import sys, pathlib, random
 ROOT = pathlib.Path(__file__).resolve().parent.parent

@@ -1,11 +1,11 @@
-"""Randomised sweep of the public entry points against the oracle (tools/fuzz_api.py): random sizes (1 x 1 ... 384 x 131, and a few that
+"""Randomised sweep of the public entry points against the oracle (tests/fuzz_api.py): random sizes (1 x 1 ... 384 x 131, and a few that
 reach the lane-per-block kernels, texture groups, the TMA-staged kernel and several pipeline chunks), formats, algorithms, weights, alpha
 weighting, over-long outputs, batches, mip chains, the compact-pixel entry point; encode and decode.  Bit-exact or it fails."""
 import pathlib, sys
 import pytest
 
 pytestmark = pytest.mark.gpu
-sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent / "tools"))
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent))
 
 
 @pytest.mark.parametrize("seed", [101, 102])
